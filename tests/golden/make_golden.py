@@ -1,0 +1,106 @@
+"""Generates the committed golden fixtures from the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+Each fixture stores the reference module's state_dict, the inputs and the reference outputs for a
+SMALL configuration of the same classes the hot path uses (full-size weights would be >50 MB);
+the kernels are config-driven, so the small shapes exercise the same code.  Zero-initialised
+layers of the reference (flow `post`, ConvFlow `proj`) are perturbed so the tests are not vacuous.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_import  # noqa: E402
+
+R = ref_import.load()
+
+
+def perturb_zero_params(m, std=0.05):
+    for _, p in m.named_parameters():
+        if float(p.abs().sum()) == 0.0:
+            p.data.normal_(0, std)
+
+
+def seq_mask(lengths, t):
+    return (torch.arange(t)[None, :] < lengths[:, None]).unsqueeze(1).float()
+
+
+def save(name, obj):
+    torch.save(obj, os.path.join(HERE, name + ".pt"))
+    print("wrote", name)
+
+
+@torch.no_grad()
+def main():
+    torch.manual_seed(1234)
+    H = R["hifigan"].HifiganGenerator
+    # 1. HiFiGAN v1 topology, narrow channels, standalone vocoder flavour
+    args = dict(in_channels=80, out_channels=1, resblock_type="1", resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                resblock_kernel_sizes=[3, 7, 11], upsample_kernel_sizes=[16, 16, 4, 4],
+                upsample_initial_channel=32, upsample_factors=[8, 8, 2, 2])
+    m = H(**args).eval()
+    x = torch.randn(2, 80, 13)
+    save("hifigan_v1_small", {"args": args, "state": m.state_dict(), "x": x, "y": m(x), "y_inference": m.inference(x)})
+    # 2. VITS flavour: cond, no weight norm on pre/post, no post bias, ResBlock2, odd sizes
+    args = dict(in_channels=24, out_channels=1, resblock_type="2", resblock_dilation_sizes=[[1, 3], [1, 3]],
+                resblock_kernel_sizes=[3, 5], upsample_kernel_sizes=[8, 4], upsample_initial_channel=48,
+                upsample_factors=[4, 2], inference_padding=0, cond_channels=12, conv_pre_weight_norm=False,
+                conv_post_weight_norm=False, conv_post_bias=False)
+    m = H(**args).eval()
+    x, g = torch.randn(3, 24, 19), torch.randn(3, 12, 1)
+    save("hifigan_cond_rb2_small", {"args": args, "state": m.state_dict(), "x": x, "g": g, "y": m(x, g)})
+    # 3. flow (reverse and forward), with speaker conditioning and ragged lengths
+    args = dict(channels=16, hidden_channels=24, kernel_size=5, dilation_rate=1, num_layers=3, num_flows=4,
+                cond_channels=10)
+    m = R["networks"].ResidualCouplingBlocks(**args).eval()
+    perturb_zero_params(m)
+    z, g = torch.randn(3, 16, 37), torch.randn(3, 10, 1)
+    mask = seq_mask(torch.tensor([37, 20, 5]), 37)
+    save("flow_small", {"args": args, "state": m.state_dict(), "z": z, "g": g, "mask": mask,
+                        "rev": m(z, mask, g=g, reverse=True), "fwd": m(z, mask, g=g, reverse=False)})
+    # 4. text encoder
+    args = dict(n_vocab=30, out_channels=16, hidden_channels=16, hidden_channels_ffn=40, num_heads=2, num_layers=3,
+                kernel_size=3, dropout_p=0.1)
+    m = R["networks"].TextEncoder(**args).eval()
+    tok = torch.randint(0, 30, (4, 23))
+    lens = torch.tensor([23, 17, 9, 2])
+    x, mp, logs, xm = m(tok, lens)
+    save("text_encoder_small", {"args": args, "state": m.state_dict(), "tokens": tok, "lengths": lens, "x": x,
+                                "m_p": mp, "logs_p": logs, "x_mask": xm})
+    # 5. stochastic duration predictor, reverse
+    args = dict(in_channels=16, hidden_channels=16, kernel_size=3, dropout_p=0.5, num_flows=4, cond_channels=10)
+    m = R["sdp"].StochasticDurationPredictor(**args).eval()
+    perturb_zero_params(m)
+    g4 = torch.randn(4, 10, 1)
+    torch.manual_seed(77)
+    noise = torch.randn(4, 2, 23)
+    torch.manual_seed(77)  # the reference draws the same tensor inside forward (sdp.py:287)
+    logw = m(x, xm, g=g4, reverse=True, noise_scale=0.8)
+    save("sdp_small", {"args": args, "state": m.state_dict(), "x": x, "x_mask": xm, "g": g4, "noise": noise,
+                       "noise_scale": 0.8, "logw": logw})
+    # 6. monotonic alignment search through the reference's own Cython kernel
+    assert R["helpers"].CYTHON, "oracle/_ref was not built (make -C oracle)"
+    cases = []
+    rng = np.random.RandomState(5)
+    for (b, tx, ty) in [(3, 7, 19), (4, 33, 70), (2, 1, 5), (2, 40, 40)]:
+        v = torch.from_numpy(rng.randn(b, tx, ty).astype(np.float32)) * 3
+        t_x = torch.from_numpy(rng.randint(1, tx + 1, size=b))
+        t_y = torch.tensor([int(rng.randint(int(a), ty + 1)) for a in t_x])
+        t_x[0], t_y[0] = tx, ty
+        mask = ((torch.arange(tx)[None, :, None] < t_x[:, None, None]) &
+                (torch.arange(ty)[None, None, :] < t_y[:, None, None])).float()
+        cases.append({"value": v, "mask": mask, "path": R["helpers"].maximum_path(v, mask)})
+    save("mas_cases", {"cases": cases})
+    # 7. generate_path: the reference's own known-answer structure (tests/tts_tests/test_helpers.py:71-88)
+    dur = torch.randint(1, 4, (10, 21)).float()
+    dur_mask = torch.ones(10, 21, int(dur.sum(1).max()))
+    save("generate_path", {"duration": dur, "mask": dur_mask, "path": R["helpers"].generate_path(dur, dur_mask)})
+
+
+if __name__ == "__main__":
+    main()

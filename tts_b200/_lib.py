@@ -1,0 +1,103 @@
+"""ctypes binding of libtts_b200.so (the C ABI in include/tts_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, the product
+path raises.  (The CPU oracle under oracle/ is test infrastructure and is never imported here.)
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtts_b200.so")
+_lib = None
+
+
+class HifiganConfigC(ctypes.Structure):
+    _fields_ = [
+        ("in_channels", ctypes.c_int),
+        ("out_channels", ctypes.c_int),
+        ("upsample_initial_channel", ctypes.c_int),
+        ("cond_channels", ctypes.c_int),
+        ("resblock_type", ctypes.c_int),
+        ("num_upsamples", ctypes.c_int),
+        ("upsample_factors", ctypes.c_int * 8),
+        ("upsample_kernel_sizes", ctypes.c_int * 8),
+        ("num_kernels", ctypes.c_int),
+        ("resblock_kernel_sizes", ctypes.c_int * 8),
+        ("num_dilations", ctypes.c_int),
+        ("resblock_dilations", (ctypes.c_int * 8) * 8),
+    ]
+
+
+def _declare(lib):
+    vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.b200tts_last_error.restype = ctypes.c_char_p
+    lib.b200tts_launch_count.restype = ctypes.c_ulonglong
+    lib.b200tts_version.restype = ci
+    lib.b200tts_mas_workspace_bytes.restype = sz
+    lib.b200tts_mas_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.b200tts_mas.restype = ci
+    lib.b200tts_mas.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp]
+    lib.b200tts_hifigan_create.restype = ci
+    lib.b200tts_hifigan_create.argtypes = [ctypes.POINTER(HifiganConfigC), ctypes.POINTER(vp), ci,
+                                           ctypes.POINTER(vp)]
+    lib.b200tts_hifigan_destroy.restype = None
+    lib.b200tts_hifigan_destroy.argtypes = [vp]
+    lib.b200tts_hifigan_workspace_bytes.restype = sz
+    lib.b200tts_hifigan_workspace_bytes.argtypes = [vp, ci, ci]
+    lib.b200tts_hifigan_out_len.restype = ci
+    lib.b200tts_hifigan_out_len.argtypes = [vp, ci]
+    lib.b200tts_hifigan_forward.restype = ci
+    lib.b200tts_hifigan_forward.argtypes = [vp, vp, vp, ci, ci, vp, vp, sz, vp]
+
+
+def lib():
+    """The loaded CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"tts_b200: {LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(tts_b200/csrc/build.sh).  There is no CPU fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200tts_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"tts_b200.{what} failed (status {rc}): {msg}")
+
+
+def ptr(t):
+    """Raw device (or host) pointer of a tensor; None -> NULL."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"tts_b200: `{name}` must be a CUDA tensor -- this package has no CPU path")
+    return t
+
+
+def launch_count():
+    return int(lib().b200tts_launch_count())
+
+
+_workspaces = {}
+
+
+def workspace(device, nbytes, tag="default"):
+    """A cached per-(device, stream, tag) scratch buffer that only ever grows."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf

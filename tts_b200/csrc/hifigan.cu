@@ -1,0 +1,195 @@
+// HiFiGAN generator engine: launch schedule over the fused conv1d kernel.
+// Reference semantics: TTS/vocoder/models/hifigan_generator.py:236-265 (HifiganGenerator.forward),
+// :84-99 (ResBlock1.forward), :150-155 (ResBlock2.forward), ctor :163-234.
+#include "engines.cuh"
+
+namespace b200tts {
+
+Hifigan::~Hifigan() {
+    free_conv(conv_pre);
+    free_conv(cond);
+    free_conv(conv_post);
+    for (auto& l : ups) free_conv(l);
+    for (auto& v : rb_c1) for (auto& l : v) free_conv(l);
+    for (auto& v : rb_c2) for (auto& l : v) free_conv(l);
+}
+
+// weights: host pointers, canonical order (see include/tts_b200.h)
+int Hifigan::init(const b200tts_hifigan_config& cfg, const float* const* w, int nw) {
+    c = cfg;
+    B200_REQUIRE(c.num_upsamples >= 1 && c.num_upsamples <= 8 && c.num_kernels >= 1 && c.num_kernels <= 8 &&
+                     c.num_dilations >= 1 && c.num_dilations <= 8,
+                 "hifigan: unsupported config");
+    const int type1 = (c.resblock_type == 1);
+    const int expect = 2 + (c.cond_channels > 0 ? 2 : 0) + 2 * c.num_upsamples +
+                       c.num_upsamples * c.num_kernels * c.num_dilations * (type1 ? 4 : 2) + 2;
+    B200_REQUIRE(nw == expect, "hifigan: expected %d weight tensors, got %d", expect, nw);
+    int i = 0;
+    int rc = pack_conv(conv_pre, w[i], w[i + 1], c.upsample_initial_channel, c.in_channels, 7, 1, 3);
+    if (rc) return rc;
+    i += 2;
+    if (c.cond_channels > 0) {
+        rc = pack_conv(cond, w[i], w[i + 1], c.upsample_initial_channel, c.cond_channels, 1, 1, 0);
+        if (rc) return rc;
+        i += 2;
+    }
+    ups.resize(c.num_upsamples);
+    rb_c1.assign(c.num_upsamples * c.num_kernels, std::vector<ConvLayer>());
+    rb_c2.assign(c.num_upsamples * c.num_kernels, std::vector<ConvLayer>());
+    int ch = c.upsample_initial_channel;
+    for (int s = 0; s < c.num_upsamples; ++s) {
+        const int u = c.upsample_factors[s], k = c.upsample_kernel_sizes[s];
+        rc = pack_conv_transpose(ups[s], w[i], w[i + 1], ch, ch / 2, k, u, (k - u) / 2);
+        if (rc) return rc;
+        i += 2;
+        ch /= 2;
+        for (int j = 0; j < c.num_kernels; ++j) {
+            const int rk = c.resblock_kernel_sizes[j];
+            auto& v1 = rb_c1[s * c.num_kernels + j];
+            auto& v2 = rb_c2[s * c.num_kernels + j];
+            v1.resize(c.num_dilations);
+            if (type1) v2.resize(c.num_dilations);
+            for (int n = 0; n < c.num_dilations; ++n) {
+                const int d = c.resblock_dilations[j][n];
+                rc = pack_conv(v1[n], w[i], w[i + 1], ch, ch, rk, d, (rk * d - d) / 2);
+                if (rc) return rc;
+                i += 2;
+                if (type1) {
+                    rc = pack_conv(v2[n], w[i], w[i + 1], ch, ch, rk, 1, (rk - 1) / 2);
+                    if (rc) return rc;
+                    i += 2;
+                }
+            }
+        }
+    }
+    rc = pack_conv(conv_post, w[i], w[i + 1], c.out_channels, ch, 7, 1, 3);
+    return rc;
+}
+
+void Hifigan::stage_dims(int T, std::vector<int>& C, std::vector<int>& L) const {
+    C.resize(c.num_upsamples);
+    L.resize(c.num_upsamples);
+    int ch = c.upsample_initial_channel, len = T;
+    for (int s = 0; s < c.num_upsamples; ++s) {
+        ch /= 2;
+        len = conv_transpose_out_len(ups[s], len);
+        C[s] = ch;
+        L[s] = len;
+    }
+}
+
+size_t Hifigan::workspace_bytes(int B, int T) const {
+    std::vector<int> C, L;
+    stage_dims(T, C, L);
+    size_t mx = 0;
+    for (size_t s = 0; s < C.size(); ++s) mx = std::max(mx, (size_t)C[s] * (size_t)L[s]);
+    size_t tot = arena_bytes((size_t)B * c.upsample_initial_channel * T);
+    tot += 4 * arena_bytes((size_t)B * mx);
+    tot += arena_bytes((size_t)B * cond.RowsPad + 64);
+    return tot;
+}
+
+int Hifigan::out_len(int T) const {
+    std::vector<int> C, L;
+    stage_dims(T, C, L);
+    return L.back();
+}
+
+int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, void* ws, size_t ws_bytes,
+                     cudaStream_t st) const {
+    B200_REQUIRE(x && wav && ws, "hifigan_forward: null pointer");
+    B200_REQUIRE((c.cond_channels > 0) == (g != nullptr) || c.cond_channels == 0,
+                 "hifigan_forward: model has cond_channels=%d but g is null", c.cond_channels);
+    B200_REQUIRE(ws_bytes >= workspace_bytes(B, T), "hifigan_forward: workspace too small");
+    if (B == 0 || T == 0) return 0;
+    std::vector<int> C, L;
+    stage_dims(T, C, L);
+    size_t mx = 0;
+    for (size_t s = 0; s < C.size(); ++s) mx = std::max(mx, (size_t)C[s] * (size_t)L[s]);
+    Arena ar(ws, ws_bytes);
+    const int C0 = c.upsample_initial_channel;
+    float* P = ar.f32((size_t)B * C0 * T);
+    float* U = ar.f32((size_t)B * mx);
+    float* T1 = ar.f32((size_t)B * mx);
+    float* R = ar.f32((size_t)B * mx);
+    float* OUT = ar.f32((size_t)B * mx);
+    float* condv = ar.f32((size_t)B * cond.RowsPad + 64);
+    B200_REQUIRE(P && U && T1 && R && OUT && condv, "hifigan_forward: arena exhausted");
+    int rc;
+    const bool has_cond = c.cond_channels > 0 && g != nullptr;
+    if (has_cond) {  // cond_layer(g): [B, cond, 1] -> [B, C0]
+        ConvIO io;
+        io.x = g; io.x_bs = c.cond_channels; io.x_cs = 1; io.Tin = 1;
+        io.y = condv; io.y_bs = cond.RowsPad; io.y_cs = 1; io.Tout = 1; io.B = B;
+        if ((rc = launch_conv(cond, io, st))) return rc;
+    }
+    {  // conv_pre (+ cond broadcast over T)
+        ConvIO io;
+        io.x = x; io.x_bs = (long long)c.in_channels * T; io.x_cs = T; io.Tin = T;
+        io.y = P; io.y_bs = (long long)C0 * T; io.y_cs = T; io.Tout = T; io.B = B;
+        if (has_cond) { io.cond = condv; io.cond_bs = cond.RowsPad; }
+        if ((rc = launch_conv(conv_pre, io, st))) return rc;
+    }
+    const float* cur = P;
+    int curC = C0, curL = T;
+    const bool type1 = c.resblock_type == 1;
+    for (int s = 0; s < c.num_upsamples; ++s) {
+        const int Cs = C[s], Ls = L[s];
+        const long long bs = (long long)Cs * Ls;
+        {  // o = ups(leaky_relu(o, 0.1))
+            ConvIO io;
+            io.x = cur; io.x_bs = (long long)curC * curL; io.x_cs = curL; io.Tin = curL; io.in_slope = 0.1f;
+            io.y = U; io.y_bs = bs; io.y_cs = Ls; io.Tout = Ls; io.B = B;
+            if ((rc = launch_conv(ups[s], io, st))) return rc;
+        }
+        for (int j = 0; j < c.num_kernels; ++j) {
+            const auto& c1 = rb_c1[s * c.num_kernels + j];
+            const auto& c2 = rb_c2[s * c.num_kernels + j];
+            const float* xin = U;
+            float* pp[2] = {R, T1};  // ping-pong for ResBlock2
+            for (int n = 0; n < c.num_dilations; ++n) {
+                const bool last = (n == c.num_dilations - 1);
+                const float* convin = xin;
+                const ConvLayer* lastconv = &c1[n];
+                if (type1) {  // T1 = c1(lrelu(xin))
+                    ConvIO io;
+                    io.x = xin; io.x_bs = bs; io.x_cs = Ls; io.Tin = Ls; io.in_slope = 0.1f;
+                    io.y = T1; io.y_bs = bs; io.y_cs = Ls; io.Tout = Ls; io.B = B;
+                    if ((rc = launch_conv(c1[n], io, st))) return rc;
+                    convin = T1;
+                    lastconv = &c2[n];
+                }
+                ConvIO io;  // xnew = conv(lrelu(convin)) + xin ; MRF: OUT (+)= xnew, mean on the last resblock
+                io.x = convin; io.x_bs = bs; io.x_cs = Ls; io.Tin = Ls; io.in_slope = 0.1f;
+                io.res = xin; io.res_bs = bs; io.res_cs = Ls;
+                io.B = B; io.Tout = Ls; io.y_bs = bs; io.y_cs = Ls;
+                float* dst;
+                if (last) {
+                    dst = OUT;
+                    if (j > 0) io.flags |= EPI_ACCUM;
+                    if (j == c.num_kernels - 1) io.post_div = (float)c.num_kernels;
+                } else {
+                    dst = type1 ? R : pp[n & 1];
+                }
+                io.y = dst;
+                if ((rc = launch_conv(*lastconv, io, st))) return rc;
+                xin = dst;
+            }
+        }
+        cur = OUT;
+        curC = Cs;
+        curL = Ls;
+        // the next stage's ups reads OUT and writes U; OUT is only rewritten by later launches
+        // on the same stream, after that read has completed.
+    }
+    {  // tanh(conv_post(leaky_relu(o)))  -- default slope 0.01 (hifigan_generator.py:262)
+        ConvIO io;
+        io.x = cur; io.x_bs = (long long)curC * curL; io.x_cs = curL; io.Tin = curL; io.in_slope = 0.01f;
+        io.y = wav; io.y_bs = (long long)c.out_channels * curL; io.y_cs = curL; io.Tout = curL; io.B = B;
+        io.act = ACT_TANH;
+        if ((rc = launch_conv(conv_post, io, st))) return rc;
+    }
+    return 0;
+}
+
+}  // namespace b200tts

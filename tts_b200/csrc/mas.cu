@@ -1,0 +1,236 @@
+// Monotonic alignment search on sm_100a.
+//
+// Reference: TTS/tts/utils/monotonic_align/core.pyx:11-37 (maximum_path_each: in-place DP over a
+// band, then a backtrack reading the DP values) and :42-47 (batch loop); caller
+// TTS/tts/utils/helpers.py:178-194 (value*mask, t_x/t_y from mask sums, int32 path).
+//
+// HBM-bound integer/compare work (8 B per cell: value in, path out) -- no tensor cores.
+// One CTA per batch item.  The y-contiguous value rows are staged through shared memory in
+// [Tx][YT] tiles with 4-byte cp.async (128 B coalesced per warp, double buffered), so the
+// column-serial DP reads shared memory conflict-free.  The "stored column" (the reference's
+// in-place value[:, y-1]) lives in a 2-deep shared array; the comparison the backtrack will need
+// (value[x,y-1] < value[x-1,y-1]) is the same pair the DP step already holds, so each step emits
+// one ballot word of direction bits per warp instead of writing DP values back to HBM.
+// The backtrack runs on one warp over those bit rows (prefetched 16 deep), then the whole CTA
+// writes the [Tx][Ty] 0/1 path with coalesced vector stores (no separate memset pass).
+//
+// Exactness: only max, one add and compares touch the data (__fadd_rn/__fmul_rn, no FMA
+// contraction), evaluated in the reference's order, so paths are bit-identical.  Cells outside
+// the band keep value*mask exactly like the reference's untouched entries, which also makes the
+// degenerate t_x > t_y case follow core.pyx (minus its unused out-of-row read at y == 0).
+#include "engines.cuh"
+
+namespace b200tts {
+
+namespace {
+
+constexpr int MAS_NT = 256;
+constexpr int MAS_DEPTH = 16;
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc));
+}
+
+struct MasArgs {
+    const float* value; const float* mask; const int* t_x; const int* t_y;
+    int B, Tx, Ty, YT, W;     // W = ceil(Tx/32) words per direction row
+    void* path; int path_is_f32;
+    unsigned* dirs_global;    // [B][Ty][W] when the bit rows do not fit in shared memory
+    int dirs_in_smem;
+    float max_neg;
+};
+
+__global__ void __launch_bounds__(MAS_NT) mas_kernel(const MasArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Tx = a.Tx, Ty = a.Ty, YT = a.YT, YS = YT + 1, W = a.W;
+    int tx = a.t_x[b], ty = a.t_y[b];
+    tx = min(max(tx, 0), Tx);
+    ty = min(max(ty, 0), Ty);
+    const bool has_mask = a.mask != nullptr;
+
+    float* tileV = reinterpret_cast<float*>(smem_raw);               // [2][Tx*YS]
+    float* tileM = tileV + 2 * Tx * YS;                              // [2][Tx*YS] (mask) or empty
+    float* col = tileM + (has_mask ? 2 * Tx * YS : 0);               // [2][Tx+1], col[.][0] unused pad
+    int* idxs = reinterpret_cast<int*>(col + 2 * (Tx + 1));          // [Ty]
+    unsigned* dirs = a.dirs_in_smem ? reinterpret_cast<unsigned*>(idxs + Ty)
+                                    : a.dirs_global + (size_t)b * Ty * W;  // [Ty][W]
+
+    const float* vb = a.value + (size_t)b * Tx * Ty;
+    const float* mbp = has_mask ? a.mask + (size_t)b * Tx * Ty : nullptr;
+    const int ytshift = 31 - __clz(YT);
+
+    auto load_tile = [&](int tile, int buf) {
+        const int y0 = tile * YT;
+        float* dv = tileV + buf * Tx * YS;
+        float* dm = tileM + buf * Tx * YS;
+        const int n = Tx << ytshift;
+        for (int i = tid; i < n; i += MAS_NT) {
+            const int x = i >> ytshift, yy = i & (YT - 1), y = y0 + yy;
+            if (y < ty) {
+                cp_async4(dv + x * YS + yy, vb + (size_t)x * Ty + y);
+                if (has_mask) cp_async4(dm + x * YS + yy, mbp + (size_t)x * Ty + y);
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    for (int x = tid; x < 2 * (Tx + 1); x += MAS_NT) col[x] = 0.f;
+
+    const int ntiles = (ty + YT - 1) / YT;
+    if (ntiles > 0) load_tile(0, 0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) {
+            load_tile(tile + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* tv = tileV + buf * Tx * YS;
+        const float* tm = tileM + buf * Tx * YS;
+        const int y0 = tile * YT;
+        const int ylim = min(YT, ty - y0);
+        for (int yy = 0; yy < ylim; ++yy) {
+            const int y = y0 + yy;
+            const float* cp = col + (y & 1) * (Tx + 1) + 1;        // stored column y-1 (index x -> cp[x])
+            float* cc = col + ((y + 1) & 1) * (Tx + 1) + 1;        // column y
+            const int lo = max(0, tx + y - ty), hi = min(tx, y + 1);
+            for (int x0 = 0; x0 < Tx; x0 += MAS_NT) {
+                const int x = x0 + tid;
+                bool dir = false;
+                if (x < Tx) {
+                    float raw = tv[x * YS + yy];
+                    if (has_mask) raw = __fmul_rn(raw, tm[x * YS + yy]);
+                    const float vc_s = cp[x];
+                    const float vp_s = cp[x - 1];                   // x == 0 reads the pad slot (unused)
+                    float nv = raw;
+                    if (x >= lo && x < hi) {
+                        const float v_cur = (x == y) ? a.max_neg : vc_s;
+                        const float v_prev = (x == 0) ? (y == 0 ? 0.f : a.max_neg) : vp_s;
+                        nv = __fadd_rn(fmaxf(v_cur, v_prev), raw);
+                    }
+                    cc[x] = nv;
+                    dir = (y > 0) && (x != 0) && (x == y || vc_s < vp_s);
+                }
+                const unsigned word = __ballot_sync(0xffffffffu, dir);
+                const int widx = (x0 >> 5) + warp;
+                if (lane == 0 && widx < W) dirs[(size_t)y * W + widx] = word;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- backtrack (warp 0)
+    if (warp == 0 && tx > 0) {
+        int index = tx - 1;
+        for (int ytop = ty - 1; ytop >= 0; ytop -= MAS_DEPTH) {
+            unsigned rows[MAS_DEPTH];
+#pragma unroll
+            for (int d = 0; d < MAS_DEPTH; ++d) {
+                const int y = ytop - d;
+                rows[d] = 0u;
+                if (y >= 1 && W <= 32) rows[d] = (lane < W) ? dirs[(size_t)y * W + lane] : 0u;
+            }
+#pragma unroll
+            for (int d = 0; d < MAS_DEPTH; ++d) {
+                const int y = ytop - d;
+                if (y < 0) break;
+                if (lane == 0) idxs[y] = index;
+                if (y >= 1) {
+                    unsigned word;
+                    if (W <= 32) word = __shfl_sync(0xffffffffu, rows[d], index >> 5);
+                    else word = dirs[(size_t)y * W + (index >> 5)];
+                    index -= (int)((word >> (index & 31)) & 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- path write: [Tx][Ty], ones at (idxs[y], y)
+    const bool valid = tx > 0;
+    if (a.path_is_f32) {
+        float* pb = reinterpret_cast<float*>(a.path) + (size_t)b * Tx * Ty;
+        for (size_t i = tid; i < (size_t)Tx * Ty; i += MAS_NT) {
+            const int x = (int)(i / Ty), y = (int)(i - (size_t)x * Ty);
+            pb[i] = (valid && y < ty && idxs[y] == x) ? 1.f : 0.f;
+        }
+    } else {
+        int* pb = reinterpret_cast<int*>(a.path) + (size_t)b * Tx * Ty;
+        if ((Ty & 3) == 0) {
+            int4* pb4 = reinterpret_cast<int4*>(pb);
+            const int Ty4 = Ty >> 2;
+            for (size_t i = tid; i < (size_t)Tx * Ty4; i += MAS_NT) {
+                const int x = (int)(i / Ty4), y = (int)(i - (size_t)x * Ty4) << 2;
+                int4 o;
+                o.x = (valid && y + 0 < ty && idxs[y + 0] == x) ? 1 : 0;
+                o.y = (valid && y + 1 < ty && idxs[y + 1] == x) ? 1 : 0;
+                o.z = (valid && y + 2 < ty && idxs[y + 2] == x) ? 1 : 0;
+                o.w = (valid && y + 3 < ty && idxs[y + 3] == x) ? 1 : 0;
+                pb4[i] = o;
+            }
+        } else {
+            for (size_t i = tid; i < (size_t)Tx * Ty; i += MAS_NT) {
+                const int x = (int)(i / Ty), y = (int)(i - (size_t)x * Ty);
+                pb[i] = (valid && y < ty && idxs[y] == x) ? 1 : 0;
+            }
+        }
+    }
+}
+
+struct MasPlan { int YT; int dirs_in_smem; size_t smem; bool ok; };
+
+MasPlan mas_plan(int Tx, int Ty, bool has_mask) {
+    MasPlan p{32, 1, 0, false};
+    const int W = (Tx + 31) / 32;
+    const size_t fixed = (size_t)2 * (Tx + 1) * 4 + (size_t)Ty * 4;
+    const size_t dirs = (size_t)Ty * W * 4;
+    for (int yt = 32; yt >= 4; yt >>= 1) {
+        const size_t tiles = (size_t)(has_mask ? 4 : 2) * Tx * (yt + 1) * 4;
+        if (tiles + fixed + dirs <= 72 * 1024) { p = {yt, 1, tiles + fixed + dirs, true}; return p; }
+    }
+    for (int yt = 32; yt >= 4; yt >>= 1) {
+        const size_t tiles = (size_t)(has_mask ? 4 : 2) * Tx * (yt + 1) * 4;
+        if (tiles + fixed <= 200 * 1024) { p = {yt, 0, tiles + fixed, true}; return p; }
+    }
+    return p;
+}
+
+}  // namespace
+
+size_t mas_workspace_bytes(int B, int Tx, int Ty) {
+    const int W = (Tx + 31) / 32;
+    return (size_t)B * Ty * W * 4 + 256;
+}
+
+int mas_forward(const float* value, const float* mask, const int* t_x, const int* t_y, int B, int Tx, int Ty,
+                void* path, int path_is_f32, void* ws, size_t ws_bytes, cudaStream_t st) {
+    B200_REQUIRE(B >= 0 && Tx >= 0 && Ty >= 0, "mas: negative size");
+    if (B == 0 || Tx == 0 || Ty == 0) return 0;
+    B200_REQUIRE(value && t_x && t_y && path, "mas: null pointer");
+    MasPlan p = mas_plan(Tx, Ty, mask != nullptr);
+    B200_REQUIRE(p.ok, "mas: Tx=%d Ty=%d does not fit the shared-memory plan", Tx, Ty);
+    B200_REQUIRE(p.dirs_in_smem || (ws && ws_bytes >= mas_workspace_bytes(B, Tx, Ty)), "mas: workspace too small");
+    static bool attr_done = false;
+    if (!attr_done) {
+        B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    MasArgs a;
+    a.value = value; a.mask = mask; a.t_x = t_x; a.t_y = t_y;
+    a.B = B; a.Tx = Tx; a.Ty = Ty; a.YT = p.YT; a.W = (Tx + 31) / 32;
+    a.path = path; a.path_is_f32 = path_is_f32;
+    a.dirs_global = reinterpret_cast<unsigned*>(ws);
+    a.dirs_in_smem = p.dirs_in_smem;
+    a.max_neg = -1e9f;
+    mas_kernel<<<B, MAS_NT, p.smem, st>>>(a);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200tts
