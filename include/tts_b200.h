@@ -81,6 +81,111 @@ int b200tts_hifigan_out_len(const b200tts_hifigan* h, int T);
 int b200tts_hifigan_forward(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- residual-coupling flow, reverse direction ------------------------------------------------
+ * Replaces ResidualCouplingBlocks.forward(reverse=True), TTS/tts/layers/vits/networks.py:214-232
+ * (blocks :138-166, WaveNet TTS/tts/layers/generic/wavenet.py:94-115) as called at vits.py:1156.
+ * weights per flow n = 0..num_flows-1 (host, PyTorch layouts, weight norm folded):
+ *   pre.w [H, C/2, 1], pre.b
+ *   enc.cond_layer.w [2*H*L, cond, 1], enc.cond_layer.b            (only if cond_channels > 0)
+ *   for each WN layer i: enc.in_layers[i].w [2H,H,k], .b, enc.res_skip_layers[i].w [2H or H,H,1], .b
+ *   post.w [C/2, H, 1], post.b
+ * z [B,C,T] is transformed IN PLACE; mask [B,T] (1/0 floats, the reference's y_mask); g [B,cond] or NULL.
+ */
+typedef struct {
+    int channels;
+    int hidden_channels;
+    int kernel_size;
+    int dilation_rate;
+    int num_layers;
+    int num_flows;
+    int cond_channels;
+} b200tts_flow_config;
+
+typedef struct b200tts_flow b200tts_flow;
+int b200tts_flow_create(const b200tts_flow_config* cfg, const float* const* weights, int num_weights,
+                        b200tts_flow** out);
+void b200tts_flow_destroy(b200tts_flow* h);
+size_t b200tts_flow_workspace_bytes(const b200tts_flow* h, int B, int T);
+int b200tts_flow_reverse(const b200tts_flow* h, float* z, const float* mask, const float* g, int B, int T,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- text encoder ----------------------------------------------------------------------------
+ * Replaces TextEncoder.forward, TTS/tts/layers/vits/networks.py:80-100 (RelativePositionTransformer
+ * TTS/tts/layers/glow_tts/transformer.py:411-432, layer_norm_type "2", heads_share=True).
+ * weights (host): emb.weight [n_vocab, hidden];
+ *   per layer l: attn.emb_rel_k [1,2w+1,d], attn.emb_rel_v, conv_q.w,.b, conv_k.w,.b, conv_v.w,.b, conv_o.w,.b,
+ *                norm_layers_1.gamma,.beta, ffn.conv_1.w,.b, ffn.conv_2.w,.b, norm_layers_2.gamma,.beta
+ *   proj.w [2*out, C, 1], proj.b                      (C = hidden_channels + language_emb_dim)
+ * tokens int64 [B,T]; lengths int64 [B]; lang_emb [B, language_emb_dim] or NULL.
+ * outputs: x [B,C,T]; stats [B,2*out,T] (m_p = rows [0,out), logs_p = rows [out,2*out)); x_mask [B,T].
+ */
+typedef struct {
+    int n_vocab;
+    int out_channels;
+    int hidden_channels;
+    int hidden_channels_ffn;
+    int num_heads;
+    int num_layers;
+    int kernel_size;
+    int rel_attn_window_size;
+    int language_emb_dim;
+} b200tts_text_encoder_config;
+
+typedef struct b200tts_text_encoder b200tts_text_encoder;
+int b200tts_text_encoder_create(const b200tts_text_encoder_config* cfg, const float* const* weights,
+                                int num_weights, b200tts_text_encoder** out);
+void b200tts_text_encoder_destroy(b200tts_text_encoder* h);
+size_t b200tts_text_encoder_workspace_bytes(const b200tts_text_encoder* h, int B, int T);
+int b200tts_text_encoder_forward(const b200tts_text_encoder* h, const int64_t* tokens, const int64_t* lengths,
+                                 const float* lang_emb, int B, int T, float* x, float* stats, float* x_mask,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stochastic duration predictor, reverse ---------------------------------------------------
+ * Replaces StochasticDurationPredictor.forward(reverse=True),
+ * TTS/tts/layers/vits/stochastic_duration_predictor.py:222-239,285-294 (+ transforms.py spline inverse).
+ * weights (host): pre.w [H,in,1], pre.b; [cond.w, cond.b]; [cond_lang.w, cond_lang.b];
+ *   convs: 3 x (convs_sep.w [H,1,k], .b, convs_1x1.w [H,H,1], .b, norms_1.gamma,.beta, norms_2.gamma,.beta);
+ *   proj.w [H,H,1], proj.b; flows.0.translation [2], flows.0.log_scale [2];
+ *   for f = 1..num_flows: flows.f.pre.w [H,1,1], .b, flows.f.convs (3 x 8 as above), flows.f.proj.w [3*nb-1,H,1], .b
+ * x [B,in,T]; mask [B,T]; noise [B,2,T] = the standard-normal draw of :287 (made by the caller so
+ * that results are reproducible against the reference); g [B,cond] / lang_emb [B,L] or NULL.
+ * logw [B,T].  err_flag: device int set to 1 if the spline discriminant goes negative (the reference
+ * asserts, transforms.py:168); may be NULL.
+ */
+typedef struct {
+    int in_channels;
+    int hidden_channels;
+    int kernel_size;
+    int num_flows;
+    int cond_channels;
+    int language_emb_dim;
+    int num_bins;
+    float tail_bound;
+} b200tts_sdp_config;
+
+typedef struct b200tts_sdp b200tts_sdp;
+int b200tts_sdp_create(const b200tts_sdp_config* cfg, const float* const* weights, int num_weights,
+                       b200tts_sdp** out);
+void b200tts_sdp_destroy(b200tts_sdp* h);
+size_t b200tts_sdp_workspace_bytes(const b200tts_sdp* h, int B, int T);
+int b200tts_sdp_reverse(const b200tts_sdp* h, const float* x, const float* mask, const float* noise, const float* g,
+                        const float* lang_emb, float noise_scale, int B, int T, float* logw, int32_t* err_flag,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- durations -> path -> expanded prior ------------------------------------------------------
+ * Replaces the glue at TTS/tts/models/vits.py:1140-1155 (generate_path: TTS/tts/utils/helpers.py:154-169).
+ * b200tts_durations : w_ceil [B,T] = ceil(exp(logw) * x_mask * length_scale); cum [B,T] = cumsum(w_ceil);
+ *                     y_lengths int64 [B] = max(1, sum(w_ceil)).
+ * b200tts_expand_prior (after the caller has read max(y_lengths) = Ty): attn [B,Tx,Ty] one-hot (or NULL),
+ *   m_p / logs_p / z_p [B,C,Ty] with z_p = m_p + noise * exp(logs_p) * noise_scale, y_mask [B,Ty] (or NULL);
+ *   stats is the text encoder's [B,2C,Tx]; noise [B,C,Ty] is the randn_like(m_p) draw of vits.py:1155.
+ */
+int b200tts_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
+                      float* cum, int64_t* y_lengths, void* stream);
+int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y_lengths, const float* stats,
+                         const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn,
+                         float* m_p, float* logs_p, float* z_p, float* y_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,23 @@ class HifiganConfigC(ctypes.Structure):
     ]
 
 
+class FlowConfigC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("channels", "hidden_channels", "kernel_size", "dilation_rate",
+                                            "num_layers", "num_flows", "cond_channels")]
+
+
+class TextEncoderConfigC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("n_vocab", "out_channels", "hidden_channels", "hidden_channels_ffn",
+                                            "num_heads", "num_layers", "kernel_size", "rel_attn_window_size",
+                                            "language_emb_dim")]
+
+
+class SdpConfigC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("in_channels", "hidden_channels", "kernel_size", "num_flows",
+                                            "cond_channels", "language_emb_dim", "num_bins")] + \
+               [("tail_bound", ctypes.c_float)]
+
+
 def _declare(lib):
     vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     lib.b200tts_last_error.restype = ctypes.c_char_p
@@ -50,6 +67,27 @@ def _declare(lib):
     lib.b200tts_hifigan_out_len.argtypes = [vp, ci]
     lib.b200tts_hifigan_forward.restype = ci
     lib.b200tts_hifigan_forward.argtypes = [vp, vp, vp, ci, ci, vp, vp, sz, vp]
+    cf = ctypes.c_float
+    for name, cfgt in (("flow", FlowConfigC), ("text_encoder", TextEncoderConfigC), ("sdp", SdpConfigC)):
+        f = getattr(lib, f"b200tts_{name}_create")
+        f.restype = ci
+        f.argtypes = [ctypes.POINTER(cfgt), ctypes.POINTER(vp), ci, ctypes.POINTER(vp)]
+        f = getattr(lib, f"b200tts_{name}_destroy")
+        f.restype = None
+        f.argtypes = [vp]
+        f = getattr(lib, f"b200tts_{name}_workspace_bytes")
+        f.restype = sz
+        f.argtypes = [vp, ci, ci]
+    lib.b200tts_flow_reverse.restype = ci
+    lib.b200tts_flow_reverse.argtypes = [vp, vp, vp, vp, ci, ci, vp, sz, vp]
+    lib.b200tts_text_encoder_forward.restype = ci
+    lib.b200tts_text_encoder_forward.argtypes = [vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, sz, vp]
+    lib.b200tts_sdp_reverse.restype = ci
+    lib.b200tts_sdp_reverse.argtypes = [vp, vp, vp, vp, vp, vp, cf, ci, ci, vp, vp, vp, sz, vp]
+    lib.b200tts_durations.restype = ci
+    lib.b200tts_durations.argtypes = [vp, vp, cf, ci, ci, vp, vp, vp, vp]
+    lib.b200tts_expand_prior.restype = ci
+    lib.b200tts_expand_prior.argtypes = [vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
 
 
 def lib():

@@ -6,6 +6,9 @@
 using namespace b200tts;
 
 struct b200tts_hifigan { Hifigan impl; };
+struct b200tts_flow { Flow impl; };
+struct b200tts_text_encoder { TextEncoder impl; };
+struct b200tts_sdp { SDP impl; };
 
 extern "C" {
 
@@ -41,6 +44,82 @@ int b200tts_hifigan_forward(const b200tts_hifigan* h, const float* x, const floa
                             void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) { set_error("hifigan_forward: null handle"); return 1; }
     return h->impl.forward(x, g, B, T, wav, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200tts_flow_create(const b200tts_flow_config* cfg, const float* const* weights, int num_weights,
+                        b200tts_flow** out) {
+    if (!cfg || !weights || !out) { set_error("flow_create: null argument"); return 1; }
+    *out = nullptr;
+    b200tts_flow* h = new (std::nothrow) b200tts_flow();
+    if (!h) { set_error("flow_create: out of host memory"); return 1; }
+    int rc = h->impl.init(*cfg, weights, num_weights);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+void b200tts_flow_destroy(b200tts_flow* h) { delete h; }
+size_t b200tts_flow_workspace_bytes(const b200tts_flow* h, int B, int T) {
+    return h ? h->impl.workspace_bytes(B, T) : 0;
+}
+int b200tts_flow_reverse(const b200tts_flow* h, float* z, const float* mask, const float* g, int B, int T,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) { set_error("flow_reverse: null handle"); return 1; }
+    return h->impl.reverse(z, mask, g, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200tts_text_encoder_create(const b200tts_text_encoder_config* cfg, const float* const* weights,
+                                int num_weights, b200tts_text_encoder** out) {
+    if (!cfg || !weights || !out) { set_error("text_encoder_create: null argument"); return 1; }
+    *out = nullptr;
+    b200tts_text_encoder* h = new (std::nothrow) b200tts_text_encoder();
+    if (!h) { set_error("text_encoder_create: out of host memory"); return 1; }
+    int rc = h->impl.init(*cfg, weights, num_weights);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+void b200tts_text_encoder_destroy(b200tts_text_encoder* h) { delete h; }
+size_t b200tts_text_encoder_workspace_bytes(const b200tts_text_encoder* h, int B, int T) {
+    return h ? h->impl.workspace_bytes(B, T) : 0;
+}
+int b200tts_text_encoder_forward(const b200tts_text_encoder* h, const int64_t* tokens, const int64_t* lengths,
+                                 const float* lang_emb, int B, int T, float* x, float* stats, float* x_mask,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) { set_error("text_encoder_forward: null handle"); return 1; }
+    return h->impl.forward((const long long*)tokens, (const long long*)lengths, lang_emb, B, T, x, stats, x_mask,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int b200tts_sdp_create(const b200tts_sdp_config* cfg, const float* const* weights, int num_weights,
+                       b200tts_sdp** out) {
+    if (!cfg || !weights || !out) { set_error("sdp_create: null argument"); return 1; }
+    *out = nullptr;
+    b200tts_sdp* h = new (std::nothrow) b200tts_sdp();
+    if (!h) { set_error("sdp_create: out of host memory"); return 1; }
+    int rc = h->impl.init(*cfg, weights, num_weights);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+void b200tts_sdp_destroy(b200tts_sdp* h) { delete h; }
+size_t b200tts_sdp_workspace_bytes(const b200tts_sdp* h, int B, int T) { return h ? h->impl.workspace_bytes(B, T) : 0; }
+int b200tts_sdp_reverse(const b200tts_sdp* h, const float* x, const float* mask, const float* noise, const float* g,
+                        const float* lang_emb, float noise_scale, int B, int T, float* logw, int32_t* err_flag,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) { set_error("sdp_reverse: null handle"); return 1; }
+    return h->impl.reverse(x, mask, noise, g, lang_emb, noise_scale, B, T, logw, err_flag, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+
+int b200tts_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
+                      float* cum, int64_t* y_lengths, void* stream) {
+    return launch_durations(logw, x_mask, length_scale, B, T, w_ceil, cum, (long long*)y_lengths, (cudaStream_t)stream);
+}
+int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y_lengths, const float* stats,
+                         const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn,
+                         float* m_p, float* logs_p, float* z_p, float* y_mask, void* stream) {
+    return launch_expand_prior(cum, x_mask, (const long long*)y_lengths, stats, noise, noise_scale, B, Tx, Ty, C, attn,
+                               m_p, logs_p, z_p, y_mask, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace b200tts {
@@ -108,8 +109,8 @@ __device__ __forceinline__ void epilogue_store(const ConvKArgs& a, int b, int r,
     *yp = v;
 }
 
-template <int CJ, int TJ, int WCO, int WT>
-__global__ void __launch_bounds__(32 * WCO * WT, 2) conv1d_kernel(const ConvKArgs a) {
+template <int CJ, int TJ, int WCO, int WT, int MINB>
+__global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvKArgs a) {
     constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT;
     extern __shared__ __align__(16) float smem[];
     const int XS = a.XS;
@@ -321,7 +322,7 @@ int pack_conv_transpose(ConvLayer& L, const float* w, const float* bias, int Cin
 }
 
 // ------------------------------------------------------------------ host: launch
-template <int CJ, int TJ, int WCO, int WT>
+template <int CJ, int TJ, int WCO, int WT, int MINB = 2>
 static int launch_variant(const ConvKArgs& ka, int B, int RowsPad, cudaStream_t st) {
     constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT;
     ConvKArgs a = ka;
@@ -330,13 +331,13 @@ static int launch_variant(const ConvKArgs& ka, int B, int RowsPad, cudaStream_t 
     B200_REQUIRE(smem <= 227 * 1024, "conv1d: K=%d dil=%d needs %zu B of shared memory", a.K, a.dil, smem);
     static bool attr_done = false;
     if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
         attr_done = true;
     }
     dim3 grid((a.Tq + T_T - 1) / T_T, RowsPad / CO_T, B);
     B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv1d: grid too large");
-    conv1d_kernel<CJ, TJ, WCO, WT><<<grid, NT, smem, st>>>(a);
+    conv1d_kernel<CJ, TJ, WCO, WT, MINB><<<grid, NT, smem, st>>>(a);
     count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -361,8 +362,13 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
                  "launch_conv: masked/split epilogue needs ymask");
     B200_REQUIRE(!(a.flags & EPI_SPLIT) || io.y2, "launch_conv: split epilogue needs y2");
     const bool small_t = a.Tq <= 128;
+    static int variant = -1;  // developer knob: B200TTS_CONV_VARIANT (0 = default)
+    if (variant < 0) { const char* e = getenv("B200TTS_CONV_VARIANT"); variant = e ? atoi(e) : 0; }
     if (L.co_tile == 64) {
         if (small_t) return launch_variant<16, 2, 4, 1>(a, io.B, L.RowsPad, st);
+        if (variant == 1) return launch_variant<16, 8, 4, 1, 3>(a, io.B, L.RowsPad, st);
+        if (variant == 2) return launch_variant<16, 8, 4, 2, 1>(a, io.B, L.RowsPad, st);
+        if (variant == 3) return launch_variant<16, 4, 4, 2, 2>(a, io.B, L.RowsPad, st);
         return launch_variant<16, 8, 4, 1>(a, io.B, L.RowsPad, st);
     }
     if (small_t) return launch_variant<16, 2, 2, 2>(a, io.B, L.RowsPad, st);

@@ -2,6 +2,7 @@
 // across streams/threads; all scratch comes from the caller's workspace.
 #pragma once
 #include <algorithm>
+#include <string.h>
 
 #include "../../include/tts_b200.h"
 #include "common.cuh"
@@ -21,6 +22,80 @@ struct Hifigan {
     int forward(const float* x, const float* g, int B, int T, float* wav, void* ws, size_t ws_bytes,
                 cudaStream_t st) const;
 };
+
+struct WaveNet {
+    int H = 0, K = 0, L = 0, cond_ch = 0;
+    ConvLayer cond;
+    std::vector<ConvLayer> in_layers, res_skip;
+    ~WaveNet();
+    int init(int hidden, int kernel_size, int dilation_rate, int num_layers, int cond_channels,
+             const float* const* w, int* consumed);
+    size_t scratch_floats(int B, int T) const;
+    int forward(float* h, float* out, const float* mask, const float* g, int B, int T, float* acts, float* condv,
+                cudaStream_t st) const;
+};
+
+struct Flow {
+    struct Block { ConvLayer pre, post; WaveNet wn; bool odd = false; };
+    b200tts_flow_config c;
+    std::vector<Block*> blocks;
+    ~Flow();
+    int init(const b200tts_flow_config& cfg, const float* const* w, int nw);
+    size_t workspace_bytes(int B, int T) const;
+    int reverse(float* z, const float* mask, const float* g, int B, int T, void* ws, size_t ws_bytes,
+                cudaStream_t st) const;
+};
+
+int launch_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, const float* mask,
+                         float* out, int B, int C, int T, float eps, cudaStream_t st);
+
+struct TextEncoder {
+    struct Layer {
+        ConvLayer qkv, o, ffn1, ffn2;
+        float *rel_k = nullptr, *rel_v = nullptr, *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    };
+    b200tts_text_encoder_config c;
+    int C = 0, d = 0;
+    float* emb = nullptr;
+    std::vector<Layer*> layers;
+    ConvLayer proj;
+    ~TextEncoder();
+    int init(const b200tts_text_encoder_config& cfg, const float* const* w, int nw);
+    size_t workspace_bytes(int B, int T) const;
+    int forward(const long long* tokens, const long long* lengths, const float* lang_emb, int B, int T, float* x,
+                float* stats, float* x_mask, void* ws, size_t ws_bytes, cudaStream_t st) const;
+};
+
+struct DDSConv {
+    int C = 0, K = 0, L = 0;
+    std::vector<ConvLayer> conv1x1;
+    std::vector<float*> sep_w, sep_b, g1, b1, g2, b2, dev;
+    ~DDSConv();
+    int init(int channels, int kernel_size, int num_layers, const float* const* w, int* consumed);
+    int forward(float* x, const float* mask, int B, int T, float* y1, float* y2, cudaStream_t st) const;
+};
+
+struct SDP {
+    struct CFlow { float *pre_w = nullptr, *pre_b = nullptr; DDSConv convs; ConvLayer proj; };
+    b200tts_sdp_config c;
+    ConvLayer pre, cond, cond_lang, proj;
+    DDSConv convs;
+    float *ea_t = nullptr, *ea_ls = nullptr;
+    std::vector<CFlow*> flows;
+    ~SDP();
+    int init(const b200tts_sdp_config& cfg, const float* const* w, int nw);
+    size_t workspace_bytes(int B, int T) const;
+    int reverse(const float* x, const float* mask, const float* noise, const float* g, const float* lang_emb,
+                float noise_scale, int B, int T, float* logw, int* err_flag, void* ws, size_t ws_bytes,
+                cudaStream_t st) const;
+};
+
+// durations -> path -> expanded prior (path.cu)
+int launch_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
+                     float* cum, long long* y_lengths, cudaStream_t st);
+int launch_expand_prior(const float* cum, const float* x_mask, const long long* y_lengths, const float* stats,
+                        const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn, float* m_p,
+                        float* logs_p, float* z_p, float* y_mask, cudaStream_t st);
 
 // monotonic alignment search (mas.cu)
 size_t mas_workspace_bytes(int B, int Tx, int Ty);
