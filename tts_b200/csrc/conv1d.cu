@@ -43,7 +43,7 @@ int upload(float** dst, const float* src, size_t n) {
 }
 
 // ------------------------------------------------------------------ device helpers
-constexpr int CI_C = 8;  // input channels per pipeline stage
+constexpr int CI_MAX = 16;  // CinPad granularity (largest input-channel chunk of any instantiation)
 
 typedef unsigned long long u64;
 
@@ -54,6 +54,11 @@ __device__ __forceinline__ void ffma2(u64& d, u64 a, float x) {
 }
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
 }
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -75,48 +80,17 @@ struct ConvKArgs {
     int XS;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
-    if (act == ACT_TANH) return tanhf(v);
-    return v;
-}
+enum : int { KEPI_GENERIC = 0, KEPI_GATE = 1, KEPI_TANH = 2, KEPI_PLAIN = 3 };
 
-// one output element through the generic epilogue (see common.cuh)
-__device__ __forceinline__ void epilogue_store(const ConvKArgs& a, int b, int r, int q, float v) {
-    if (r >= a.Rows) return;
-    v += a.bias[r];
-    if (a.cond) v += __ldg(a.cond + b * a.cond_bs + r);
-    v = apply_act(v, a.act);
-    int ch = r, t = q;
-    if (a.ups > 1) { ch = r / a.ups; t = q * a.ups + (r - ch * a.ups); }
-    if (t >= a.Tout) return;
-    const float m = a.ymask ? __ldg(a.ymask + b * a.ymask_bs + t) : 1.f;
-    float* yp; bool accum, mask_post;
-    if (a.flags & EPI_SPLIT) {
-        if (ch < a.split) { yp = a.y + b * a.y_bs + (long long)ch * a.y_cs + t; accum = true; mask_post = true; }
-        else { yp = a.y2 + b * a.y2_bs + (long long)(ch - a.split) * a.y2_cs + t; accum = (a.flags & EPI_ACCUM2) != 0; mask_post = false; }
-    } else {
-        yp = a.y + b * a.y_bs + (long long)ch * a.y_cs + t;
-        accum = (a.flags & EPI_ACCUM) != 0;
-        mask_post = (a.flags & EPI_MASK_POST) != 0;
-    }
-    if (a.flags & EPI_MASK_PRE) v *= m;
-    if (a.res) v += a.res[b * a.res_bs + (long long)ch * a.res_cs + t];  // may alias y (in-place residual)
-    v *= a.scale;
-    if (accum) v += *yp;
-    if (a.post_div != 1.f) v = v / a.post_div;
-    if (mask_post) v *= m;
-    *yp = v;
-}
-
-template <int CJ, int TJ, int WCO, int WT, int MINB>
-__global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvKArgs a) {
+// CJ rows x TJ time steps per lane, WCO x WT warps, CIC input channels per stage, EPI epilogue family
+template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI>
+__global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d_kernel(const ConvKArgs a) {
     constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT;
     extern __shared__ __align__(16) float smem[];
     const int XS = a.XS;
-    const int wchunk = CI_C * a.K * CO_T;
+    const int wchunk = CIC * a.K * CO_T;
     float* xs0 = smem;
-    float* ws0 = smem + 2 * CI_C * XS;
+    float* ws0 = smem + 2 * CIC * XS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wco = warp % WCO, wt = warp / WCO;
     const int b = blockIdx.z, tile_co = blockIdx.y;
@@ -125,7 +99,7 @@ __global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvK
     const float* xb = a.x + b * a.x_bs;
     const float* mb = a.xmask ? a.xmask + b * a.xmask_bs : nullptr;
     const float* wg = a.w + (size_t)tile_co * a.CinPad * a.K * CO_T;
-    const int nchunks = a.CinPad / CI_C;
+    const int nchunks = (a.Cin + CIC - 1) / CIC;   // CinPad is a multiple of CI_MAX >= CIC; skip all-zero chunks
     const float slope = a.in_slope;
 
     auto load_chunk = [&](int chunk, int buf) {
@@ -133,24 +107,27 @@ __global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvK
         float* dst = ws0 + buf * wchunk;
         for (int i = tid * 4; i < wchunk; i += NT * 4) cp_async16(dst + i, src + i);
         cp_async_commit();
-        float* xd = xs0 + buf * CI_C * XS;
-        const int c0 = chunk * CI_C;
+        float* xd = xs0 + buf * CIC * XS;
+        const int c0 = chunk * CIC;
         for (int i = tid; i < XS; i += NT) {
             const int t = tin0 + i;
             const bool tok = (t >= 0) && (t < a.Tin);
             float m = 1.f;
             if (tok && mb) m = __ldg(mb + t);
-            float v[CI_C];
 #pragma unroll
-            for (int ci = 0; ci < CI_C; ++ci) {
-                v[ci] = 0.f;
-                if (tok && (c0 + ci) < a.Cin) v[ci] = __ldg(xb + (long long)(c0 + ci) * a.x_cs + t);
-            }
+            for (int h = 0; h < CIC; h += 8) {
+                float v[8];
 #pragma unroll
-            for (int ci = 0; ci < CI_C; ++ci) {
-                float u = v[ci] * m;
-                u = u > 0.f ? u : u * slope;
-                xd[ci * XS + i] = u;
+                for (int ci = 0; ci < 8; ++ci) {
+                    v[ci] = 0.f;
+                    if (tok && (c0 + h + ci) < a.Cin) v[ci] = __ldg(xb + (long long)(c0 + h + ci) * a.x_cs + t);
+                }
+#pragma unroll
+                for (int ci = 0; ci < 8; ++ci) {
+                    float u = v[ci] * m;
+                    u = u > 0.f ? u : u * slope;
+                    xd[(h + ci) * XS + i] = u;
+                }
             }
         }
     };
@@ -169,16 +146,14 @@ __global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvK
     for (int ch = 0; ch < nchunks; ++ch) {
         const int buf = ch & 1;
         if (ch + 1 < nchunks) load_chunk(ch + 1, buf ^ 1);
-        const float* xr = xs0 + buf * CI_C * XS + wt * 32 * TJ + lane;
+        const float* xr = xs0 + buf * CIC * XS + wt * 32 * TJ + lane;
         const float* wr = ws0 + buf * wchunk + wco * CJ;
 #pragma unroll 1
-        for (int ci = 0; ci < CI_C; ++ci) {
-            const float* xp0 = xr + ci * XS;
-            const float* wp0 = wr + ci * K * CO_T;
-#pragma unroll 2
+        for (int ci = 0; ci < CIC; ++ci) {
+            const float* xp = xr + ci * XS;
+            const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(wr + ci * K * CO_T);
+#pragma unroll 1
             for (int k = 0; k < K; ++k) {
-                const float* xp = xp0 + k * dil;
-                const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(wp0 + k * CO_T);
                 float xv[TJ];
 #pragma unroll
                 for (int j = 0; j < TJ; ++j) xv[j] = xp[32 * j];
@@ -193,6 +168,8 @@ __global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvK
                 for (int j = 0; j < TJ; ++j)
 #pragma unroll
                     for (int p = 0; p < CJ / 2; ++p) ffma2(acc[p][j], wv[p], xv[j]);
+                xp += dil;
+                wp += CO_T / 4;
             }
         }
         cp_async_wait_all();
@@ -202,37 +179,183 @@ __global__ void __launch_bounds__(32 * WCO * WT, MINB) conv1d_kernel(const ConvK
     // ---------------------------------------------------------------- epilogue
     const int row_base = tile_co * CO_T + wco * CJ;
     const int qb = q0 + wt * 32 * TJ + lane;
-    if (a.flags & EPI_GATE) {
-        // rows (2p, 2p+1) = (tanh half, sigmoid half) of output row row_base/2 + p
+    if (EPI == KEPI_GATE) {
+        // rows (2p, 2p+1) = (tanh half, sigmoid half) of output row row_base/2 + p   (wavenet.py:6-13)
 #pragma unroll
         for (int p = 0; p < CJ / 2; ++p) {
             const int r0 = row_base + 2 * p;
-            if (r0 + 1 >= a.Rows) continue;
-            float b0 = a.bias[r0], b1 = a.bias[r0 + 1];
-            if (a.cond) { b0 += __ldg(a.cond + b * a.cond_bs + r0); b1 += __ldg(a.cond + b * a.cond_bs + r0 + 1); }
-            float* yrow = a.y + b * a.y_bs + (long long)(r0 >> 1) * a.y_cs;
+            if (r0 + 1 < a.Rows) {
+                float b0 = a.bias[r0], b1 = a.bias[r0 + 1];
+                if (a.cond) { b0 += __ldg(a.cond + b * a.cond_bs + r0); b1 += __ldg(a.cond + b * a.cond_bs + r0 + 1); }
+                float* yrow = a.y + b * a.y_bs + (long long)(r0 >> 1) * a.y_cs;
 #pragma unroll
-            for (int j = 0; j < TJ; ++j) {
-                const int q = qb + 32 * j;
-                if (q >= a.Tout) continue;
-                float v0, v1;
-                unpack2(acc[p][j], v0, v1);
-                v0 += b0; v1 += b1;
-                yrow[q] = tanhf(v0) * (1.f / (1.f + expf(-v1)));
+                for (int j = 0; j < TJ; ++j) {
+                    const int q = qb + 32 * j;
+                    float v0, v1;
+                    unpack2(acc[p][j], v0, v1);
+                    v0 += b0; v1 += b1;
+                    if (q < a.Tout) yrow[q] = tanhf(v0) * (1.f / (1.f + expf(-v1)));
+                }
             }
         }
         return;
     }
+    if (EPI == KEPI_TANH) {   // conv_post: y = tanh(acc + bias)   (hifigan_generator.py:263-264)
 #pragma unroll
-    for (int p = 0; p < CJ / 2; ++p) {
+        for (int p = 0; p < CJ / 2; ++p) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = row_base + 2 * p + h;
+                if (r < a.Rows) {
+                    const float bb = a.bias[r];
+                    float* yrow = a.y + b * a.y_bs + (long long)r * a.y_cs;
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) {
+                        const int q = qb + 32 * j;
+                        float v0, v1;
+                        unpack2(acc[p][j], v0, v1);
+                        if (q < a.Tout) yrow[q] = tanhf((h ? v1 : v0) + bb);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    if (EPI == KEPI_PLAIN) {   // y = act(acc + bias + cond) [* mask]   -- no residual / accumulate / upsampling
+        const bool relu_p = a.act == ACT_RELU;
+        float mkp[TJ];
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
             const int q = qb + 32 * j;
-            if (q >= a.Tq) continue;
+            mkp[j] = (a.ymask && q < a.Tout) ? __ldg(a.ymask + b * a.ymask_bs + q) : 1.f;
+        }
+#pragma unroll
+        for (int p = 0; p < CJ / 2; ++p) {
+            const int r0 = row_base + 2 * p;
+            float b0 = 0.f, b1 = 0.f;
+            if (r0 < a.Rows) { b0 = a.bias[r0]; if (a.cond) b0 += __ldg(a.cond + b * a.cond_bs + r0); }
+            if (r0 + 1 < a.Rows) { b1 = a.bias[r0 + 1]; if (a.cond) b1 += __ldg(a.cond + b * a.cond_bs + r0 + 1); }
+            float* y0 = a.y + b * a.y_bs + (long long)r0 * a.y_cs;
+            float* y1 = y0 + a.y_cs;
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                const int q = qb + 32 * j;
+                float v0, v1;
+                unpack2(acc[p][j], v0, v1);
+                v0 += b0; v1 += b1;
+                if (relu_p) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                v0 *= mkp[j]; v1 *= mkp[j];
+                if (q < a.Tout) {
+                    if (r0 < a.Rows) y0[q] = v0;
+                    if (r0 + 1 < a.Rows) y1[q] = v1;
+                }
+            }
+        }
+        return;
+    }
+    // generic: v = act(acc + bias + cond) [*m] [+res] *scale [+y_old] [/div] [*m]; all loads are issued before
+    // any store (res / y_old may alias y only element-for-element, never across threads)
+    const int ups = a.ups;
+    const bool relu = a.act == ACT_RELU;
+    const bool split = (a.flags & EPI_SPLIT) != 0;
+    float mk[TJ];
+    int tq[TJ];
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) {
+        tq[j] = (qb + 32 * j) * ups;
+        mk[j] = 1.f;
+        if (a.ymask && ups == 1 && tq[j] < a.Tout) mk[j] = __ldg(a.ymask + b * a.ymask_bs + tq[j]);
+    }
+    // per-row destination: recomputed per phase instead of kept in registers (16 rows x 2 pointers would spill)
+    auto rowinfo = [&](int i, float*& yp, const float*& rp, bool& accum, bool& mpost) -> bool {
+        const int r = row_base + i;
+        int chn = r, ph = 0;
+        if (ups > 1) { chn = r / ups; ph = r - chn * ups; }
+        accum = (a.flags & EPI_ACCUM) != 0;
+        mpost = (a.flags & EPI_MASK_POST) != 0;
+        yp = a.y + b * a.y_bs + (long long)chn * a.y_cs + ph;
+        if (split) {
+            if (chn < a.split) { accum = true; mpost = true; }
+            else { yp = a.y2 + b * a.y2_bs + (long long)(chn - a.split) * a.y2_cs; accum = (a.flags & EPI_ACCUM2) != 0; mpost = false; }
+        }
+        rp = a.res ? a.res + b * a.res_bs + (long long)chn * a.res_cs + ph : nullptr;
+        return r < a.Rows;
+    };
+    const bool mpre = (a.flags & EPI_MASK_PRE) != 0;
+    // phase 1: bias / cond / activation / pre-mask (registers only)
+#pragma unroll
+    for (int p = 0; p < CJ / 2; ++p) {
+        const int r0 = row_base + 2 * p;
+        float b0 = 0.f, b1 = 0.f;
+        if (r0 < a.Rows) { b0 = a.bias[r0]; if (a.cond) b0 += __ldg(a.cond + b * a.cond_bs + r0); }
+        if (r0 + 1 < a.Rows) { b1 = a.bias[r0 + 1]; if (a.cond) b1 += __ldg(a.cond + b * a.cond_bs + r0 + 1); }
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
             float v0, v1;
             unpack2(acc[p][j], v0, v1);
-            epilogue_store(a, b, row_base + 2 * p, q, v0);
-            epilogue_store(a, b, row_base + 2 * p + 1, q, v1);
+            v0 += b0; v1 += b1;
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (mpre) { v0 *= mk[j]; v1 *= mk[j]; }
+            acc[p][j] = pack2(v0, v1);
+        }
+    }
+    // phase 2: residual (all loads first)
+    if (a.res) {
+#pragma unroll
+        for (int p = 0; p < CJ / 2; ++p) {
+            float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1;
+            const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1);
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                float v0, v1, r0v = 0.f, r1v = 0.f;
+                if (ok0 && tq[j] < a.Tout) r0v = rp0[tq[j]];
+                if (ok1 && tq[j] < a.Tout) r1v = rp1[tq[j]];
+                unpack2(acc[p][j], v0, v1);
+                acc[p][j] = pack2(v0 + r0v, v1 + r1v);
+            }
+        }
+    }
+    // phase 3: scale, accumulate into the destination (all loads first)
+    const float scale = a.scale;
+    if (split || (a.flags & EPI_ACCUM)) {
+#pragma unroll
+        for (int p = 0; p < CJ / 2; ++p) {
+            float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1;
+            const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1);
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                float v0, v1, o0 = 0.f, o1 = 0.f;
+                if (ac0 && ok0 && tq[j] < a.Tout) o0 = yp0[tq[j]];
+                if (ac1 && ok1 && tq[j] < a.Tout) o1 = yp1[tq[j]];
+                unpack2(acc[p][j], v0, v1);
+                acc[p][j] = pack2(v0 * scale + o0, v1 * scale + o1);
+            }
+        }
+    } else if (scale != 1.f) {
+#pragma unroll
+        for (int p = 0; p < CJ / 2; ++p)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                float v0, v1;
+                unpack2(acc[p][j], v0, v1);
+                acc[p][j] = pack2(v0 * scale, v1 * scale);
+            }
+    }
+    // phase 4: mean / post-mask / store
+    const float div = a.post_div;
+#pragma unroll
+    for (int p = 0; p < CJ / 2; ++p) {
+        float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1;
+        const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1);
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            float v0, v1;
+            unpack2(acc[p][j], v0, v1);
+            if (div != 1.f) { v0 = v0 / div; v1 = v1 / div; }
+            if (mp0) v0 *= mk[j];
+            if (mp1) v1 *= mk[j];
+            if (ok0 && tq[j] < a.Tout) yp0[tq[j]] = v0;
+            if (ok1 && tq[j] < a.Tout) yp1[tq[j]] = v1;
         }
     }
 }
@@ -253,7 +376,7 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
     L.co_tile = rows >= 64 ? 64 : 32;
     L.RowsPad = round_up(rows, L.co_tile);
     L.Cin = Cin;
-    L.CinPad = round_up(Cin, CI_C);
+    L.CinPad = round_up(Cin, CI_MAX);
     L.K = K;
     const int T = L.co_tile, ntile = L.RowsPad / T;
     std::vector<float> P((size_t)ntile * L.CinPad * K * T, 0.f);
@@ -322,25 +445,43 @@ int pack_conv_transpose(ConvLayer& L, const float* w, const float* bias, int Cin
 }
 
 // ------------------------------------------------------------------ host: launch
-template <int CJ, int TJ, int WCO, int WT, int MINB = 2>
+template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI>
 static int launch_variant(const ConvKArgs& ka, int B, int RowsPad, cudaStream_t st) {
     constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT;
     ConvKArgs a = ka;
     a.XS = round_up(T_T + (a.K - 1) * a.dil, 4);
-    const size_t smem = (size_t)(2 * CI_C * a.XS + 2 * CI_C * a.K * CO_T) * sizeof(float);
+    const size_t smem = (size_t)(2 * CIC * a.XS + 2 * CIC * a.K * CO_T) * sizeof(float);
     B200_REQUIRE(smem <= 227 * 1024, "conv1d: K=%d dil=%d needs %zu B of shared memory", a.K, a.dil, smem);
     static bool attr_done = false;
     if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     dim3 grid((a.Tq + T_T - 1) / T_T, RowsPad / CO_T, B);
     B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv1d: grid too large");
-    conv1d_kernel<CJ, TJ, WCO, WT, MINB><<<grid, NT, smem, st>>>(a);
+    conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI><<<grid, NT, smem, st>>>(a);
     count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <int CIC, int EPI>
+static int launch_tiles(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaStream_t st) {
+    const bool small_t = a.Tq <= 128;
+    if (co_tile == 64) {
+        if (small_t) return launch_variant<16, 2, 4, 1, CIC, EPI>(a, B, RowsPad, st);
+        return launch_variant<16, 4, 4, 2, CIC, EPI>(a, B, RowsPad, st);
+    }
+    if (small_t) return launch_variant<16, 2, 2, 2, CIC, EPI>(a, B, RowsPad, st);
+    return launch_variant<16, 4, 2, 4, CIC, EPI>(a, B, RowsPad, st);
+}
+
+template <int EPI>
+static int launch_cic(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaStream_t st) {
+    // keep the work per pipeline stage roughly constant: CIC * K ~ 48..112 tap-steps
+    if (a.K >= 9) return launch_tiles<8, EPI>(a, co_tile, B, RowsPad, st);
+    return launch_tiles<16, EPI>(a, co_tile, B, RowsPad, st);
 }
 
 int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
@@ -361,18 +502,20 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     B200_REQUIRE(!(a.flags & (EPI_MASK_PRE | EPI_MASK_POST | EPI_SPLIT)) || io.ymask,
                  "launch_conv: masked/split epilogue needs ymask");
     B200_REQUIRE(!(a.flags & EPI_SPLIT) || io.y2, "launch_conv: split epilogue needs y2");
-    const bool small_t = a.Tq <= 128;
-    static int variant = -1;  // developer knob: B200TTS_CONV_VARIANT (0 = default)
-    if (variant < 0) { const char* e = getenv("B200TTS_CONV_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (L.co_tile == 64) {
-        if (small_t) return launch_variant<16, 2, 4, 1>(a, io.B, L.RowsPad, st);
-        if (variant == 1) return launch_variant<16, 8, 4, 1, 3>(a, io.B, L.RowsPad, st);
-        if (variant == 2) return launch_variant<16, 8, 4, 2, 1>(a, io.B, L.RowsPad, st);
-        if (variant == 3) return launch_variant<16, 4, 4, 2, 2>(a, io.B, L.RowsPad, st);
-        return launch_variant<16, 8, 4, 1>(a, io.B, L.RowsPad, st);
+    B200_REQUIRE(!(io.ymask && L.ups > 1), "launch_conv: output mask with an upsampling layer is not supported");
+    if (a.flags & EPI_GATE) {
+        B200_REQUIRE(L.ups == 1 && !io.res && a.act == ACT_NONE, "launch_conv: gate epilogue takes no other options");
+        return launch_cic<KEPI_GATE>(a, L.co_tile, io.B, L.RowsPad, st);
     }
-    if (small_t) return launch_variant<16, 2, 2, 2>(a, io.B, L.RowsPad, st);
-    return launch_variant<16, 8, 2, 2>(a, io.B, L.RowsPad, st);
+    if (a.act == ACT_TANH) {
+        B200_REQUIRE(L.ups == 1 && !io.res && !io.cond && a.flags == 0 && a.scale == 1.f && a.post_div == 1.f,
+                     "launch_conv: tanh epilogue takes no other options");
+        return launch_cic<KEPI_TANH>(a, L.co_tile, io.B, L.RowsPad, st);
+    }
+    const bool plain = L.ups == 1 && !io.res && a.scale == 1.f && a.post_div == 1.f &&
+                       (a.flags & ~(EPI_MASK_POST | EPI_MASK_PRE)) == 0;
+    if (plain) return launch_cic<KEPI_PLAIN>(a, L.co_tile, io.B, L.RowsPad, st);
+    return launch_cic<KEPI_GENERIC>(a, L.co_tile, io.B, L.RowsPad, st);
 }
 
 }  // namespace b200tts
