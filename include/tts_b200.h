@@ -186,6 +186,27 @@ int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y
                          const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn,
                          float* m_p, float* logs_p, float* z_p, float* y_mask, void* stream);
 
+/* ---- STFT magnitude / mel front end ----------------------------------------------------------
+ * Replaces wav_to_spec / spec_to_mel / wav_to_mel, TTS/tts/models/vits.py:96-208, and TorchSTFT.__call__,
+ * TTS/utils/audio/torch_transforms.py:104-145.
+ * create: window [n_fft] (host; the analysis window already zero-padded to n_fft), mel_basis [n_mels, n_fft/2+1]
+ *         (host, e.g. librosa.filters.mel) or NULL.  n_fft must be a power of two.
+ * magnitude: wav [B,T] -> spec [B, n_fft/2+1, n_frames].  The signal is reflect-padded by pad1 samples, then by
+ *   pad2 samples (both each side; 0 = none), then framed with hop (no centering of its own):
+ *     wav_to_spec  : pad1 = (n_fft-hop)/2, pad2 = 0,        mode 0: sqrt(re^2+im^2+1e-6)
+ *     TorchSTFT    : pad1 = pad_wav ? (n_fft-hop)/2 : 0, pad2 = n_fft/2 (center=True), mode 1: sqrt(max(.,1e-8))
+ *   power != 1 raises the magnitude to that power (TorchSTFT.power).
+ * mel_project: mel [B,n_mels,n_frames] = basis @ spec, followed by log(max(., log_clamp)) when log_clamp > 0.
+ */
+typedef struct b200tts_stft b200tts_stft;
+int b200tts_stft_create(int n_fft, int hop_length, const float* window, const float* mel_basis, int n_mels,
+                        b200tts_stft** out);
+void b200tts_stft_destroy(b200tts_stft* h);
+int b200tts_stft_magnitude(const b200tts_stft* h, const float* wav, int B, int T, int pad1, int pad2, int mode,
+                           float power, float* spec, int n_frames, void* stream);
+int b200tts_stft_mel_project(const b200tts_stft* h, const float* spec, int B, int n_frames, float log_clamp,
+                             float* mel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,14 @@ def _declare(lib):
         f = getattr(lib, f"b200tts_{name}_workspace_bytes")
         f.restype = sz
         f.argtypes = [vp, ci, ci]
+    lib.b200tts_stft_create.restype = ci
+    lib.b200tts_stft_create.argtypes = [ci, ci, vp, vp, ci, ctypes.POINTER(vp)]
+    lib.b200tts_stft_destroy.restype = None
+    lib.b200tts_stft_destroy.argtypes = [vp]
+    lib.b200tts_stft_magnitude.restype = ci
+    lib.b200tts_stft_magnitude.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, vp, ci, vp]
+    lib.b200tts_stft_mel_project.restype = ci
+    lib.b200tts_stft_mel_project.argtypes = [vp, vp, ci, ci, cf, vp, vp]
     lib.b200tts_flow_reverse.restype = ci
     lib.b200tts_flow_reverse.argtypes = [vp, vp, vp, vp, ci, ci, vp, sz, vp]
     lib.b200tts_text_encoder_forward.restype = ci

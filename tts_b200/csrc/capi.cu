@@ -9,6 +9,7 @@ struct b200tts_hifigan { Hifigan impl; };
 struct b200tts_flow { Flow impl; };
 struct b200tts_text_encoder { TextEncoder impl; };
 struct b200tts_sdp { SDP impl; };
+struct b200tts_stft { Stft impl; };
 
 extern "C" {
 
@@ -120,6 +121,29 @@ int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y
                          float* m_p, float* logs_p, float* z_p, float* y_mask, void* stream) {
     return launch_expand_prior(cum, x_mask, (const long long*)y_lengths, stats, noise, noise_scale, B, Tx, Ty, C, attn,
                                m_p, logs_p, z_p, y_mask, (cudaStream_t)stream);
+}
+
+int b200tts_stft_create(int n_fft, int hop_length, const float* window, const float* mel_basis, int n_mels,
+                        b200tts_stft** out) {
+    if (!out) { set_error("stft_create: null argument"); return 1; }
+    *out = nullptr;
+    b200tts_stft* h = new (std::nothrow) b200tts_stft();
+    if (!h) { set_error("stft_create: out of host memory"); return 1; }
+    int rc = h->impl.init(n_fft, hop_length, window, mel_basis, n_mels);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+void b200tts_stft_destroy(b200tts_stft* h) { delete h; }
+int b200tts_stft_magnitude(const b200tts_stft* h, const float* wav, int B, int T, int pad1, int pad2, int mode,
+                           float power, float* spec, int n_frames, void* stream) {
+    if (!h) { set_error("stft_magnitude: null handle"); return 1; }
+    return h->impl.magnitude(wav, B, T, pad1, pad2, mode, power, spec, n_frames, (cudaStream_t)stream);
+}
+int b200tts_stft_mel_project(const b200tts_stft* h, const float* spec, int B, int n_frames, float log_clamp,
+                             float* mel, void* stream) {
+    if (!h) { set_error("stft_mel_project: null handle"); return 1; }
+    return h->impl.mel_project(spec, B, n_frames, log_clamp, mel, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -52,7 +52,7 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 //            SPLIT (WN res/skip): rows <  split -> (y , accum=1, mask_post=1)
 //                                 rows >= split -> (y2, accum=accum2, no mask), row index -= split
 //            ups > 1 (polyphase transposed conv): row r -> channel r/ups, time q*ups + r%ups
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_LOGCLAMP = 3 };  // LOGCLAMP: log(max(v, act_param))
 enum : int { EPI_GATE = 1, EPI_MASK_PRE = 2, EPI_MASK_POST = 4, EPI_ACCUM = 8, EPI_SPLIT = 16, EPI_ACCUM2 = 32 };
 
 struct ConvLayer {            // immutable after pack(); owned by an engine handle
@@ -79,6 +79,7 @@ struct ConvIO {
     float scale = 1.0f;
     float post_div = 1.0f;   // applied after accumulation (MRF mean: z_sum / num_kernels)
     int act = ACT_NONE;
+    float act_param = 0.f;
     int flags = 0;
     int B = 1;
 };

@@ -76,7 +76,7 @@ struct ConvKArgs {
     const float* res; long long res_bs; int res_cs;
     const float* ymask; long long ymask_bs;
     float* y2; long long y2_bs; int y2_cs; int split;
-    float scale; float post_div; int act; int flags;
+    float scale; float post_div; int act; float act_param; int flags;
     int XS;
 };
 
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
     }
     if (EPI == KEPI_PLAIN) {   // y = act(acc + bias + cond) [* mask]   -- no residual / accumulate / upsampling
         const bool relu_p = a.act == ACT_RELU;
+        const bool logc_p = a.act == ACT_LOGCLAMP;
         float mkp[TJ];
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
                 unpack2(acc[p][j], v0, v1);
                 v0 += b0; v1 += b1;
                 if (relu_p) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                if (logc_p) { v0 = logf(fmaxf(v0, a.act_param)); v1 = logf(fmaxf(v1, a.act_param)); }
                 v0 *= mkp[j]; v1 *= mkp[j];
                 if (q < a.Tout) {
                     if (r0 < a.Rows) y0[q] = v0;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
         if (a.ymask && ups == 1 && tq[j] < a.Tout) mk[j] = __ldg(a.ymask + b * a.ymask_bs + tq[j]);
     }
     // per-row destination: recomputed per phase instead of kept in registers (16 rows x 2 pointers would spill)
-    auto rowinfo = [&](int i, float*& yp, const float*& rp, bool& accum, bool& mpost) -> bool {
+    auto rowinfo = [&](int i, float*& yp, const float*& rp, bool& accum, bool& mpost, int& tlim) -> bool {
         const int r = row_base + i;
         int chn = r, ph = 0;
         if (ups > 1) { chn = r / ups; ph = r - chn * ups; }
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
             else { yp = a.y2 + b * a.y2_bs + (long long)(chn - a.split) * a.y2_cs; accum = (a.flags & EPI_ACCUM2) != 0; mpost = false; }
         }
         rp = a.res ? a.res + b * a.res_bs + (long long)chn * a.res_cs + ph : nullptr;
+        tlim = a.Tout - ph;   // element (q*ups + ph) exists iff q*ups < Tout - ph
         return r < a.Rows;
     };
     const bool mpre = (a.flags & EPI_MASK_PRE) != 0;
@@ -303,13 +306,13 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
     if (a.res) {
 #pragma unroll
         for (int p = 0; p < CJ / 2; ++p) {
-            float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1;
-            const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1);
+            float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1; int tl0, tl1;
+            const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0, tl0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1, tl1);
 #pragma unroll
             for (int j = 0; j < TJ; ++j) {
                 float v0, v1, r0v = 0.f, r1v = 0.f;
-                if (ok0 && tq[j] < a.Tout) r0v = rp0[tq[j]];
-                if (ok1 && tq[j] < a.Tout) r1v = rp1[tq[j]];
+                if (ok0 && tq[j] < tl0) r0v = rp0[tq[j]];
+                if (ok1 && tq[j] < tl1) r1v = rp1[tq[j]];
                 unpack2(acc[p][j], v0, v1);
                 acc[p][j] = pack2(v0 + r0v, v1 + r1v);
             }
@@ -320,13 +323,13 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
     if (split || (a.flags & EPI_ACCUM)) {
 #pragma unroll
         for (int p = 0; p < CJ / 2; ++p) {
-            float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1;
-            const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1);
+            float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1; int tl0, tl1;
+            const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0, tl0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1, tl1);
 #pragma unroll
             for (int j = 0; j < TJ; ++j) {
                 float v0, v1, o0 = 0.f, o1 = 0.f;
-                if (ac0 && ok0 && tq[j] < a.Tout) o0 = yp0[tq[j]];
-                if (ac1 && ok1 && tq[j] < a.Tout) o1 = yp1[tq[j]];
+                if (ac0 && ok0 && tq[j] < tl0) o0 = yp0[tq[j]];
+                if (ac1 && ok1 && tq[j] < tl1) o1 = yp1[tq[j]];
                 unpack2(acc[p][j], v0, v1);
                 acc[p][j] = pack2(v0 * scale + o0, v1 * scale + o1);
             }
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
     const float div = a.post_div;
 #pragma unroll
     for (int p = 0; p < CJ / 2; ++p) {
-        float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1;
-        const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1);
+        float *yp0, *yp1; const float *rp0, *rp1; bool ac0, ac1, mp0, mp1; int tl0, tl1;
+        const bool ok0 = rowinfo(2 * p, yp0, rp0, ac0, mp0, tl0), ok1 = rowinfo(2 * p + 1, yp1, rp1, ac1, mp1, tl1);
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
             float v0, v1;
@@ -354,8 +357,8 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
             if (div != 1.f) { v0 = v0 / div; v1 = v1 / div; }
             if (mp0) v0 *= mk[j];
             if (mp1) v1 *= mk[j];
-            if (ok0 && tq[j] < a.Tout) yp0[tq[j]] = v0;
-            if (ok1 && tq[j] < a.Tout) yp1[tq[j]] = v1;
+            if (ok0 && tq[j] < tl0) yp0[tq[j]] = v0;
+            if (ok1 && tq[j] < tl1) yp1[tq[j]] = v1;
         }
     }
 }
@@ -497,7 +500,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     a.res = io.res; a.res_bs = io.res_bs; a.res_cs = io.res_cs;
     a.ymask = io.ymask; a.ymask_bs = io.ymask_bs;
     a.y2 = io.y2; a.y2_bs = io.y2_bs; a.y2_cs = io.y2_cs; a.split = io.split;
-    a.scale = io.scale; a.post_div = io.post_div; a.act = io.act; a.flags = io.flags;
+    a.scale = io.scale; a.post_div = io.post_div; a.act = io.act; a.act_param = io.act_param; a.flags = io.flags;
     if (a.Tq <= 0 || io.B <= 0) return 0;
     B200_REQUIRE(!(a.flags & (EPI_MASK_PRE | EPI_MASK_POST | EPI_SPLIT)) || io.ymask,
                  "launch_conv: masked/split epilogue needs ymask");
@@ -515,6 +518,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     const bool plain = L.ups == 1 && !io.res && a.scale == 1.f && a.post_div == 1.f &&
                        (a.flags & ~(EPI_MASK_POST | EPI_MASK_PRE)) == 0;
     if (plain) return launch_cic<KEPI_PLAIN>(a, L.co_tile, io.B, L.RowsPad, st);
+    B200_REQUIRE(a.act != ACT_LOGCLAMP, "launch_conv: log-clamp activation only with the plain epilogue");
     return launch_cic<KEPI_GENERIC>(a, L.co_tile, io.B, L.RowsPad, st);
 }
 

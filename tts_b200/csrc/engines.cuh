@@ -90,6 +90,17 @@ struct SDP {
                 cudaStream_t st) const;
 };
 
+struct Stft {
+    int n_fft = 0, hop = 0, log2n = 0, n_mels = 0;
+    float *window = nullptr, *twiddle = nullptr;
+    ConvLayer mel;
+    ~Stft();
+    int init(int n_fft, int hop, const float* window_host, const float* mel_basis_host, int n_mels);
+    int magnitude(const float* wav, int B, int T, int pad1, int pad2, int mode, float power, float* spec, int n_frames,
+                  cudaStream_t st) const;
+    int mel_project(const float* spec, int B, int n_frames, float log_clamp, float* out, cudaStream_t st) const;
+};
+
 // durations -> path -> expanded prior (path.cu)
 int launch_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
                      float* cum, long long* y_lengths, cudaStream_t st);
