@@ -159,15 +159,9 @@ def run_cuda(args):
     def gather(wav, y_lengths):
         if world == 1:
             return
-        # one collective on the data path: rank 0 gathers the (padded) waveforms + lengths over NVLink
-        tmax = torch.tensor([wav.shape[-1]], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        pad = torch.zeros((wav.shape[0], 1, int(tmax.item())), device=dev)
-        pad[..., : wav.shape[-1]] = wav
-        outs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        lens = [torch.empty_like(y_lengths) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, outs, dst=0)
-        dist.gather(y_lengths, lens, dst=0)
+        # the one collective on the data path: rank 0 gathers the (padded) waveforms + lengths over NVLink
+        from tts_b200.parallel import gather_waveforms
+        gather_waveforms(wav, y_lengths * 256, dst=0)
 
     def step_resident(stage_events=None):
         model._stage_events = stage_events
