@@ -273,12 +273,14 @@ def run_cuda(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv1d_kernel (all HiFiGAN launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "conv1d_tc_kernel + conv1d_kernel (all HiFiGAN launches of a step)",
                          "achieved": dec_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (dec_tflops / peaks["bf16_tflops_sustained"]) if dec_tflops else None,
                          "traffic": None, "peak_source": peaks["source"],
-                         "note": "FP32 FMA-pipe (FFMA2) kernel, no tensor-core use yet; against the measured FP32 FMA "
-                                 f"peak of {FP32_FMA_PEAK_TFLOPS} TFLOP/s the fraction is frac_fp32_fma",
+                         "note": "algorithmic fp32 FLOPs; the MRF/pre convs run on tcgen05 kind::tf32 as 3xTF32 (3 MMAs per "
+                                 "algorithmic MAC at half the bf16 rate => ceiling = peak/6), upsamplers/post on the FP32 "
+                                 f"FMA pipe (measured peak {FP32_FMA_PEAK_TFLOPS} TFLOP/s)",
+                         "frac_of_3xtf32_ceiling": (dec_tflops / (peaks["bf16_tflops_sustained"] / 6.0)) if dec_tflops else None,
                          "frac_fp32_fma": (dec_tflops / FP32_FMA_PEAK_TFLOPS) if dec_tflops else None},
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"2 of {B_PER_GPU} utterances, one step ({cpu_samples} samples, {cpu_sec:.2f} s)"},

@@ -30,6 +30,8 @@ const char* b200tts_last_error(void);
 /* number of kernels launched by this library in this process (bench.py "gpu_launches") */
 unsigned long long b200tts_launch_count(void);
 int b200tts_version(void);
+/* debug aid: 1 if a tcgen05 conv launch ever hit a pipeline timeout (synchronises the device) */
+int b200tts_debug_tc_error(void);
 
 /* ---- monotonic alignment search ------------------------------------------------------------
  * Replaces maximum_path_c / maximum_path_each, TTS/tts/utils/monotonic_align/core.pyx:11-47

@@ -1,13 +1,15 @@
 """CUDA HiFiGAN generator vs golden fixtures (reference outputs) and vs the oracle at full width.
-north_star tolerance: waveform within 1e-4 RMS; asserted here an order of magnitude tighter."""
+north_star tolerance: waveform within 1e-4 RMS.  The decoder convs run on the tcgen05 3xTF32 kernel (fp32
+accumulate in TMEM, ~2^-25 truncation per accumulation step), so the asserted bound is 3e-5 RMS; with
+B200TTS_NO_TC=1 (FP32 FMA kernel only) the same tests hold at 1e-6."""
 import pytest
 import torch
 
 import vits_oracle as O
 
 pytestmark = pytest.mark.gpu
-RMS_TOL = 1e-5
-MAX_TOL = 1e-4
+RMS_TOL = 3e-5
+MAX_TOL = 3e-4
 
 
 def _close(got, want):

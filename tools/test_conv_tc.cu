@@ -1,0 +1,160 @@
+// Standalone validation + timing of the tcgen05 3xTF32 conv kernel against a double-accumulating reference kernel.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/test_conv_tc tools/test_conv_tc.cu
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../tts_b200/csrc/conv_tc.cuh"
+
+using namespace b200tts::tc;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+__global__ void ref_conv(const float* x, const float* w, const float* bias, const float* res, const float* yold, float* y,
+                         int C, int Cout, int T, int K, int dil, int pad, float slope, float scale, int accum) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x, co = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    double acc = 0;
+    for (int ci = 0; ci < C; ++ci)
+        for (int k = 0; k < K; ++k) {
+            int ti = t + k * dil - pad;
+            if (ti < 0 || ti >= T) continue;
+            float v = x[((size_t)b * C + ci) * T + ti];
+            v = v > 0 ? v : v * slope;
+            acc += (double)v * (double)w[((size_t)co * C + ci) * K + k];
+        }
+    float u = (float)acc + bias[co];
+    size_t o = ((size_t)b * Cout + co) * T + t;
+    if (res) u += res[o];
+    u *= scale;
+    if (accum) u += yold[o];
+    y[o] = u;
+}
+
+static std::vector<float> pack_tc(const std::vector<float>& W, int Cout, int Cin, int K, int N) {
+    const int ntile = (Cout + N - 1) / N, nchunk = (Cin + KC - 1) / KC;
+    const size_t blk = (size_t)2 * NSLAB * N * 4;  // floats per (tile, chunk, tap)
+    std::vector<float> P((size_t)ntile * nchunk * K * blk, 0.f);
+    for (int tile = 0; tile < ntile; ++tile)
+        for (int c = 0; c < nchunk; ++c)
+            for (int k = 0; k < K; ++k) {
+                float* dst = P.data() + (((size_t)tile * nchunk + c) * K + k) * blk;
+                for (int s = 0; s < NSLAB; ++s)
+                    for (int n = 0; n < N; ++n)
+                        for (int i = 0; i < 4; ++i) {
+                            const int co = tile * N + n, ci = c * KC + 4 * s + i;
+                            float v = (co < Cout && ci < Cin) ? W[((size_t)co * Cin + ci) * K + k] : 0.f;
+                            uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u;
+                            float hi; memcpy(&hi, &u, 4);
+                            dst[((size_t)s * N + n) * 4 + i] = hi;
+                            dst[((size_t)(NSLAB + s) * N + n) * 4 + i] = v - hi;
+                        }
+            }
+    return P;
+}
+
+static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum, int iters) {
+    const int Cout = C, pad = (K * dil - dil) / 2;
+    const int N = Cout > 128 ? 128 : Cout;
+    printf("case B=%d C=%d T=%d K=%d dil=%d res=%d accum=%d N=%d: ", B, C, T, K, dil, with_res, accum, N);
+    fflush(stdout);
+    srand(1234 + C + K);
+    std::vector<float> hx((size_t)B * C * T), hw((size_t)Cout * C * K), hb(Cout), hr((size_t)B * Cout * T), hy0((size_t)B * Cout * T);
+    for (auto& v : hx) v = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+    for (auto& v : hw) v = (rand() / (float)RAND_MAX - 0.5f) * 0.2f;
+    for (auto& v : hb) v = (rand() / (float)RAND_MAX - 0.5f);
+    for (auto& v : hr) v = (rand() / (float)RAND_MAX - 0.5f);
+    for (auto& v : hy0) v = (rand() / (float)RAND_MAX - 0.5f);
+    std::vector<float> hp = pack_tc(hw, Cout, C, K, N);
+    float *dx, *dw, *dp, *db, *dr, *dy, *dyr; int* derr;
+    CK(cudaMalloc(&dx, hx.size() * 4)); CK(cudaMalloc(&dw, hw.size() * 4)); CK(cudaMalloc(&dp, hp.size() * 4));
+    CK(cudaMalloc(&db, hb.size() * 4)); CK(cudaMalloc(&dr, hr.size() * 4)); CK(cudaMalloc(&dy, hy0.size() * 4));
+    CK(cudaMalloc(&dyr, hy0.size() * 4)); CK(cudaMalloc(&derr, 4)); CK(cudaMemset(derr, 0, 4));
+    CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dp, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dr, hr.data(), hr.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy, hy0.data(), hy0.size() * 4, cudaMemcpyHostToDevice));
+    const float slope = 0.1f, scale = accum ? 1.f : 1.f;
+    ref_conv<<<dim3((T + 127) / 128, Cout, B), 128>>>(dx, dw, db, with_res ? dr : nullptr, dy, dyr, C, Cout, T, K, dil, pad, slope, scale, accum);
+    CK(cudaDeviceSynchronize());
+    TcArgs a; memset(&a, 0, sizeof(a));
+    a.x = dx; a.x_bs = (long long)C * T; a.x_cs = T; a.Tin = T; a.in_slope = slope;
+    a.w = dp; a.bias = db; a.Cin = C; a.K = K; a.dil = dil; a.pad = pad; a.Rows = Cout; a.N = N;
+    a.y = dy; a.y_bs = (long long)Cout * T; a.y_cs = T; a.Tout = T;
+    if (with_res) { a.res = dr; a.res_bs = (long long)Cout * T; a.res_cs = T; }
+    a.scale = scale; a.post_div = 1.f; a.accum = accum; a.err = derr;
+    a.sleep_ns = getenv("TC_SLEEP") ? atoi(getenv("TC_SLEEP")) : 0;
+    a.dbg = getenv("TC_DBG") ? atoi(getenv("TC_DBG")) : 0;
+    a.rows_pad = (TT + (K - 1) * dil + 7) / 8 * 8;
+    const size_t smem = smem_bytes(N, a.rows_pad);
+    CK(cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    dim3 grid((T + TT - 1) / TT, (Cout + N - 1) / N, B);
+    conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("KERNEL FAILED: %s\n", cudaGetErrorString(e)); return 1; }
+    int herr = 0; CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+    std::vector<float> hy(hy0.size()), hyr(hy0.size());
+    CK(cudaMemcpy(hy.data(), dy, hy.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hyr.data(), dyr, hy.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0, sumsq = 0;
+    for (size_t i = 0; i < hy.size(); ++i) {
+        double d = fabs((double)hy[i] - (double)hyr[i]);
+        if (d > maxerr) maxerr = d;
+        if (fabs(hyr[i]) > maxref) maxref = fabs(hyr[i]);
+        sumsq += d * d;
+    }
+    printf("smem=%zu err_flag=%d max_err=%.3e rms_err=%.3e max_ref=%.3f  %s", smem, herr, maxerr, sqrt(sumsq / hy.size()), maxref,
+           (herr == 0 && maxerr < 1e-4 * (maxref + 1)) ? "OK" : "MISMATCH");
+    if (getenv("TC_TRACE")) {
+        const size_t nb = (size_t)grid.x * grid.y * grid.z;
+        unsigned long long* dtr; CK(cudaMalloc(&dtr, nb * 16 * 8)); CK(cudaMemset(dtr, 0, nb * 16 * 8));
+        a.trace = dtr;
+        conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a);
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned long long> tr(nb * 16);
+        CK(cudaMemcpy(tr.data(), dtr, nb * 16 * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull; for (size_t i = 0; i < nb; ++i) if (tr[i * 16 + 11] && tr[i * 16 + 11] < t0) t0 = tr[i * 16 + 11];
+        printf("\ntrace (us since first CTA start): blk start alloc_done prodA0 prodB0 prodAend prodBend acc_full epi_end mma_start mma_firstA mma_end dealloc\n");
+        for (size_t i : {(size_t)0, (size_t)1, nb / 3, nb / 2, nb - 2, nb - 1}) {
+            const unsigned long long* r = &tr[i * 16];
+            auto us = [&](int k) { return r[k] ? (double)(r[k] - t0) / 1e3 : -1.0; };
+            printf("  blk %5zu: %8.1f %8.1f | %8.1f %8.1f %8.1f %8.1f | %8.1f %8.1f | %8.1f %8.1f %8.1f | %8.1f || c2: issue %8.1f data %8.1f stored %8.1f arrived %8.1f\n", i, us(11), us(0), us(1), us(2), us(3), us(4), us(5), us(6), us(7), us(8), us(9), us(10), us(12), us(13), us(14), us(15));
+        }
+        a.trace = nullptr;
+    }
+    if (iters > 0 && herr == 0 && !accum) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a);
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+        printf("  %.3f ms  %.1f TFLOP/s (algorithmic fp32)", ms, 2.0 * B * Cout * (double)C * K * T / ms / 1e9);
+    }
+    printf("\n");
+    cudaFree(dx); cudaFree(dw); cudaFree(dp); cudaFree(db); cudaFree(dr); cudaFree(dy); cudaFree(dyr); cudaFree(derr);
+    return (herr == 0 && maxerr < 1e-4 * (maxref + 1)) ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+    int fails = 0;
+    if (argc >= 8 && !strcmp(argv[1], "one"))
+        return run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 1, 0, atoi(argv[7]));
+    fails += run_case(1, 32, 256, 1, 1, 0, 0, 0);      // smallest: one chunk group, one tap
+    fails += run_case(1, 32, 300, 3, 1, 0, 0, 0);
+    fails += run_case(2, 128, 700, 11, 5, 1, 0, 0);
+    fails += run_case(2, 256, 300, 3, 3, 1, 1, 0);
+    fails += run_case(2, 64, 1000, 7, 3, 0, 0, 0);
+    if (fails == 0 || (argc > 1 && !strcmp(argv[1], "time"))) {
+        run_case(32, 128, 9600, 11, 5, 1, 0, 5);       // HiFiGAN stage 1 at cfg2
+        run_case(32, 128, 9600, 3, 1, 1, 0, 5);
+        run_case(32, 256, 1200, 7, 3, 1, 0, 5);
+        run_case(32, 64, 19200, 11, 1, 1, 0, 5);
+        run_case(32, 32, 38400, 7, 1, 1, 0, 5);
+    }
+    printf("FAILS=%d\n", fails);
+    return fails;
+}

@@ -16,6 +16,7 @@ extern "C" {
 const char* b200tts_last_error(void) { return last_error(); }
 unsigned long long b200tts_launch_count(void) { return g_launch_count; }
 int b200tts_version(void) { return 100; }
+int b200tts_debug_tc_error(void) { return conv_tc_error_flag(); }
 
 size_t b200tts_mas_workspace_bytes(int B, int Tx, int Ty) { return mas_workspace_bytes(B, Tx, Ty); }
 

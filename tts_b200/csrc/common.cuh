@@ -64,6 +64,10 @@ struct ConvLayer {            // immutable after pack(); owned by an engine hand
     int ups = 1;              // >1: polyphase ConvTranspose1d
     int co_tile = 64;         // 32 or 64
     int tr_kernel = 0, tr_pad = 0;  // original transposed-conv kernel size / padding (for Tout)
+    float* w_tc = nullptr;    // device, tcgen05 packing [n_tile][chunk][tap]{hi,lo}[slab][N][4] (null: layer not eligible)
+    int tc_n = 0;             // columns (output rows) per tcgen05 CTA
+    bool allow_tc = false;    // engines opt layers into the 3xTF32 tensor-core path (decoder / flow); the text and
+                              // duration path stays on the exact FP32 FMA kernel so durations remain bit-stable
 };
 
 struct ConvIO {
@@ -93,6 +97,7 @@ int pack_conv_transpose(ConvLayer& L, const float* w, const float* bias, int Cin
                         int padding);
 void free_conv(ConvLayer& L);
 int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
+int conv_tc_error_flag();
 inline int conv_transpose_out_len(const ConvLayer& L, int Tin) {
     return (Tin - 1) * L.ups - 2 * L.tr_pad + L.tr_kernel;
 }

@@ -15,6 +15,7 @@
 // broadcasts), accumulating row pairs with fma.rn.f32x2 (SASS FFMA2, x as broadcast scalar).
 // Bias / conditioning / gate / residual / mask / MRF-accumulate epilogues are fused.
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -369,7 +370,8 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 void free_conv(ConvLayer& L) {
     if (L.w) cudaFree(L.w);
     if (L.bias) cudaFree(L.bias);
-    L.w = L.bias = nullptr;
+    if (L.w_tc) cudaFree(L.w_tc);
+    L.w = L.bias = L.w_tc = nullptr;
 }
 
 // Wl(r, ci, k): logical weights already expressed as a correlation-form conv with `rows` GEMM rows
@@ -393,6 +395,36 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
     for (int r = 0; r < rows; ++r) bp[r] = bl[r];
     if (upload(&L.w, P.data(), P.size())) return 2;
     if (upload(&L.bias, bp.data(), bp.size())) return 2;
+    // tcgen05 packing (3xTF32 hi/lo split) for layers the tensor-core kernel can take
+    L.tc_n = 0;
+    for (int n : {128, 64, 32, 16}) if (rows % n == 0) { L.tc_n = n; break; }
+    if (L.tc_n && rows >= 32 && Cin >= 8) {
+        using namespace tc;
+        const int N = L.tc_n, nt = rows / N, nchunk = (Cin + KC - 1) / KC;
+        const size_t blk = (size_t)2 * NSLAB * N * 4;
+        std::vector<float> Q((size_t)nt * nchunk * K * blk, 0.f);
+        for (int tile = 0; tile < nt; ++tile)
+            for (int c = 0; c < nchunk; ++c)
+                for (int k = 0; k < K; ++k) {
+                    float* dst = Q.data() + (((size_t)tile * nchunk + c) * K + k) * blk;
+                    for (int s2 = 0; s2 < NSLAB; ++s2)
+                        for (int n = 0; n < N; ++n)
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = tile * N + n, ci = c * KC + 4 * s2 + i;
+                                const float v = (ci < Cin) ? Wl[((size_t)r * Cin + ci) * K + k] : 0.f;
+                                uint32_t u;
+                                memcpy(&u, &v, 4);
+                                u &= 0xFFFFE000u;
+                                float hi;
+                                memcpy(&hi, &u, 4);
+                                dst[((size_t)s2 * N + n) * 4 + i] = hi;
+                                dst[((size_t)(NSLAB + s2) * N + n) * 4 + i] = v - hi;
+                            }
+                }
+        if (upload(&L.w_tc, Q.data(), Q.size())) return 2;
+    } else {
+        L.tc_n = 0;
+    }
     return 0;
 }
 
@@ -487,6 +519,51 @@ static int launch_cic(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaS
     return launch_tiles<16, EPI>(a, co_tile, B, RowsPad, st);
 }
 
+// tcgen05 path: returns -1 when the layer / shape / epilogue is not eligible (caller falls through to the FMA kernel)
+static int* g_tc_err = nullptr;
+static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("B200TTS_NO_TC"); enabled = (e && atoi(e)) ? 0 : 1; }
+    if (!enabled || !L.allow_tc || !L.w_tc || L.ups != 1 || a.Tq < 128) return -1;
+    if (a.act == ACT_LOGCLAMP || (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2))) return -1;
+    const int rows_pad = (tc::TT + (L.K - 1) * L.dil + 7) / 8 * 8;
+    if (tc::NSLAB * rows_pad > tc::MAXIT * tc::PGROUP) return -1;
+    const size_t smem = tc::smem_bytes(L.tc_n, rows_pad);
+    if (smem > 227 * 1024) return -1;
+    static bool init_done = false;
+    if (!init_done) {
+        B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaMalloc((void**)&g_tc_err, sizeof(int)));
+        B200_CUDA_OK(cudaMemset(g_tc_err, 0, sizeof(int)));
+        init_done = true;
+    }
+    tc::TcArgs t;
+    memset(&t, 0, sizeof(t));
+    t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin;
+    t.xmask = a.xmask; t.xmask_bs = a.xmask_bs; t.in_slope = a.in_slope;
+    t.w = L.w_tc; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
+    t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = L.tc_n;
+    t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout;
+    t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
+    t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;
+    t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
+    t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
+    t.rows_pad = rows_pad; t.err = g_tc_err;
+    dim3 grid((a.Tq + tc::TT - 1) / tc::TT, L.Rows / L.tc_n, io.B);
+    if (grid.y > 65535 || grid.z > 65535) return -1;
+    tc::conv1d_tc_kernel<<<grid, tc::NTHREADS, smem, st>>>(t);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int conv_tc_error_flag() {   // 1 if any tcgen05 launch hit a pipeline timeout (debug aid; synchronises)
+    if (!g_tc_err) return 0;
+    int h = 0;
+    cudaMemcpy(&h, g_tc_err, sizeof(int), cudaMemcpyDeviceToHost);
+    return h;
+}
+
 int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     B200_REQUIRE(L.w && io.x && io.y, "launch_conv: null tensor");
     ConvKArgs a;
@@ -515,6 +592,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
                      "launch_conv: tanh epilogue takes no other options");
         return launch_cic<KEPI_TANH>(a, L.co_tile, io.B, L.RowsPad, st);
     }
+    if (int rc = try_launch_tc(L, io, a, st); rc != -1) return rc;
     const bool plain = L.ups == 1 && !io.res && a.scale == 1.f && a.post_div == 1.f &&
                        (a.flags & ~(EPI_MASK_POST | EPI_MASK_PRE)) == 0;
     if (plain) return launch_cic<KEPI_PLAIN>(a, L.co_tile, io.B, L.RowsPad, st);
