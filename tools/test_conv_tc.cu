@@ -6,7 +6,8 @@
 #include <string.h>
 #include <vector>
 
-#include "../tts_b200/csrc/conv_tc.cuh"
+#include "../tts_b200/csrc/conv_tc2.cuh"
+#include "../tts_b200/csrc/conv_tc3.cuh"
 
 using namespace b200tts::tc;
 
@@ -57,7 +58,8 @@ static std::vector<float> pack_tc(const std::vector<float>& W, int Cout, int Cin
 
 static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum, int iters) {
     const int Cout = C, pad = (K * dil - dil) / 2;
-    const int N = Cout > 128 ? 128 : Cout;
+    const bool v3 = getenv("TC_V3") != nullptr;
+    const int N = v3 ? 128 : (Cout > 128 ? 128 : Cout);
     printf("case B=%d C=%d T=%d K=%d dil=%d res=%d accum=%d N=%d: ", B, C, T, K, dil, with_res, accum, N);
     fflush(stdout);
     srand(1234 + C + K);
@@ -93,7 +95,41 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     const size_t smem = smem_bytes(N, a.rows_pad);
     CK(cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid((T + TT - 1) / TT, (Cout + N - 1) / N, B);
-    conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a);
+    const bool v2 = getenv("TC_V2") != nullptr;
+    b200tts::tc3::Tc3Args a3; memset(&a3, 0, sizeof(a3));
+    b200tts::tc2::Tc2Args a2; memset(&a2, 0, sizeof(a2));
+    size_t smem2 = 0; dim3 grid2(1);
+    if (v3) {
+        using namespace b200tts::tc3;
+        a3.x = dx; a3.x_bs = a.x_bs; a3.x_cs = T; a3.Tin = T; a3.in_slope = slope; a3.w = dp; a3.bias = db;
+        a3.Cin = C; a3.K = K; a3.dil = dil; a3.pad = pad; a3.Rows = Cout; a3.N = 128;
+        a3.y = dy; a3.y_bs = a.y_bs; a3.y_cs = T; a3.Tout = T; a3.ups = 1; a3.Tq = T;
+        a3.res = a.res; a3.res_bs = a.res_bs; a3.res_cs = a.res_cs; a3.scale = scale; a3.post_div = 1.f; a3.accum = accum;
+        a3.rows_pad = a.rows_pad; a3.raw_w = a.rows_pad + 4; a3.B = B; a3.n_ttiles = (T + 255) / 256; a3.n_rtiles = (Cout + 127) / 128;
+        a3.err = derr;
+        smem2 = smem_bytes3(a3.rows_pad, a3.raw_w);
+        CK(cudaFuncSetAttribute(conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int tiles = a3.B * a3.n_ttiles * a3.n_rtiles;
+        grid2 = dim3(tiles < sms ? tiles : sms);
+        conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+    } else if (v2) {
+        using namespace b200tts::tc2;
+        a2.x = dx; a2.x_bs = a.x_bs; a2.x_cs = T; a2.Tin = T; a2.in_slope = slope; a2.w = dp; a2.bias = db;
+        a2.Cin = C; a2.K = K; a2.dil = dil; a2.pad = pad; a2.Rows = Cout; a2.N = N;
+        a2.y = dy; a2.y_bs = a.y_bs; a2.y_cs = T; a2.Tout = T; a2.ups = 1; a2.Tq = T;
+        a2.res = a.res; a2.res_bs = a.res_bs; a2.res_cs = a.res_cs; a2.scale = scale; a2.post_div = 1.f; a2.accum = accum;
+        a2.rows_pad = a.rows_pad; a2.raw_w = a.rows_pad + 4; a2.B = B; a2.n_ttiles = (T + TT2 - 1) / TT2; a2.n_rtiles = (Cout + N - 1) / N;
+        a2.err = derr; a2.tg = taps_per_slot(N);
+        smem2 = smem_bytes2(N, a2.rows_pad, a2.raw_w);
+        CK(cudaFuncSetAttribute(conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const int tiles = a2.B * a2.n_ttiles * a2.n_rtiles;
+        grid2 = dim3(tiles < sms ? tiles : sms);
+        conv1d_tc2_kernel<<<grid2, NTHREADS2, smem2>>>(a2);
+    } else {
+        conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("KERNEL FAILED: %s\n", cudaGetErrorString(e)); return 1; }
     int herr = 0; CK(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
@@ -107,9 +143,39 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
         if (fabs(hyr[i]) > maxref) maxref = fabs(hyr[i]);
         sumsq += d * d;
     }
-    printf("smem=%zu err_flag=%d max_err=%.3e rms_err=%.3e max_ref=%.3f  %s", smem, herr, maxerr, sqrt(sumsq / hy.size()), maxref,
+    printf("%s smem=%zu err_flag=%d max_err=%.3e rms_err=%.3e max_ref=%.3f  %s", v3 ? "v3" : (v2 ? "v2" : "v1"), (v2 || v3) ? smem2 : smem, herr, maxerr, sqrt(sumsq / hy.size()), maxref,
            (herr == 0 && maxerr < 1e-4 * (maxref + 1)) ? "OK" : "MISMATCH");
-    if (getenv("TC_TRACE")) {
+    if (getenv("TC_TRACE") && v3) {
+        unsigned long long* dtr; CK(cudaMalloc(&dtr, (size_t)grid2.x * 32 * 8)); CK(cudaMemset(dtr, 0, (size_t)grid2.x * 32 * 8));
+        a3.trace = dtr;
+        b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned long long> tr((size_t)grid2.x * 32);
+        CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
+        printf("\nv3 trace (us since CTA start): prod: chunk0 tile0 tile1 tile3 end | mma: tile0 tile1 tile3 end | epi: t0[start,end] t1[start,end] t3[start,end] end\n");
+        for (int blk : {0, (int)grid2.x - 1}) {
+            const unsigned long long* r = &tr[(size_t)blk * 32];
+            auto us = [&](int k) { return r[k] ? (double)(r[k] - r[0]) / 1e3 : -1.0; };
+            printf("  cta %3d: %6.1f %6.1f %6.1f %6.1f %7.1f | %6.1f %6.1f %6.1f %7.1f | [%6.1f %6.1f] [%6.1f %6.1f] [%6.1f %6.1f] %7.1f\n", blk,
+                   us(1), us(2), us(3), us(4), us(5), us(8), us(9), us(10), us(11), us(16), us(17), us(18), us(19), us(20), us(21), us(22));
+        }
+        a3.trace = nullptr;
+    } else if (getenv("TC_TRACE") && v2) {
+        unsigned long long* dtr; CK(cudaMalloc(&dtr, (size_t)grid2.x * 32 * 8)); CK(cudaMemset(dtr, 0, (size_t)grid2.x * 32 * 8));
+        a2.trace = dtr;
+        b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2);
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned long long> tr((size_t)grid2.x * 32);
+        CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
+        printf("\nv2 trace (us since CTA start): prod: chunk0 tile0 tile1 tile3 end | mma: tile0 tile1 tile3 end | epi: t0[start,end] t1[start,end] t3[start,end] end\n");
+        for (int blk : {0, 1, (int)grid2.x / 2, (int)grid2.x - 1}) {
+            const unsigned long long* r = &tr[(size_t)blk * 32];
+            auto us = [&](int k) { return r[k] ? (double)(r[k] - r[0]) / 1e3 : -1.0; };
+            printf("  cta %3d: %6.1f %6.1f %6.1f %6.1f %7.1f | %6.1f %6.1f %6.1f %7.1f | [%6.1f %6.1f] [%6.1f %6.1f] [%6.1f %6.1f] %7.1f\n", blk,
+                   us(1), us(2), us(3), us(4), us(5), us(8), us(9), us(10), us(11), us(16), us(17), us(18), us(19), us(20), us(21), us(22));
+        }
+        a2.trace = nullptr;
+    } else if (getenv("TC_TRACE")) {
         const size_t nb = (size_t)grid.x * grid.y * grid.z;
         unsigned long long* dtr; CK(cudaMalloc(&dtr, nb * 16 * 8)); CK(cudaMemset(dtr, 0, nb * 16 * 8));
         a.trace = dtr;
@@ -129,7 +195,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (iters > 0 && herr == 0 && !accum) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        for (int i = 0; i < iters; ++i) conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a);
+        for (int i = 0; i < iters; ++i) { if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
         printf("  %.3f ms  %.1f TFLOP/s (algorithmic fp32)", ms, 2.0 * B * Cout * (double)C * K * T / ms / 1e9);

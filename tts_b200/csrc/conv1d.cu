@@ -16,6 +16,8 @@
 // Bias / conditioning / gate / residual / mask / MRF-accumulate epilogues are fused.
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
 
 #include <stdarg.h>
 #include <stdlib.h>
@@ -396,11 +398,14 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
     if (upload(&L.w, P.data(), P.size())) return 2;
     if (upload(&L.bias, bp.data(), bp.size())) return 2;
     // tcgen05 packing (3xTF32 hi/lo split) for layers the tensor-core kernel can take
+    // rows >= 64: tiles of 128 zero-padded rows (tcgen05 M = 128, third-generation kernel); narrower layers keep
+    // exact tiles of 32 / 16 rows for the M = time orientation
     L.tc_n = 0;
-    for (int n : {128, 64, 32, 16}) if (rows % n == 0) { L.tc_n = n; break; }
-    if (L.tc_n && rows >= 32 && Cin >= 8) {
+    if (rows >= 64) L.tc_n = 128;
+    else for (int n : {32, 16}) if (rows % n == 0) { L.tc_n = n; break; }
+    if (L.tc_n && rows >= 16 && Cin >= 8) {
         using namespace tc;
-        const int N = L.tc_n, nt = rows / N, nchunk = (Cin + KC - 1) / KC;
+        const int N = L.tc_n, nt = (rows + N - 1) / N, nchunk = (Cin + KC - 1) / KC;
         const size_t blk = (size_t)2 * NSLAB * N * 4;
         std::vector<float> Q((size_t)nt * nchunk * K * blk, 0.f);
         for (int tile = 0; tile < nt; ++tile)
@@ -411,7 +416,7 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
                         for (int n = 0; n < N; ++n)
                             for (int i = 0; i < 4; ++i) {
                                 const int r = tile * N + n, ci = c * KC + 4 * s2 + i;
-                                const float v = (ci < Cin) ? Wl[((size_t)r * Cin + ci) * K + k] : 0.f;
+                                const float v = (ci < Cin && r < rows) ? Wl[((size_t)r * Cin + ci) * K + k] : 0.f;
                                 uint32_t u;
                                 memcpy(&u, &v, 4);
                                 u &= 0xFFFFE000u;
@@ -522,21 +527,82 @@ static int launch_cic(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaS
 // tcgen05 path: returns -1 when the layer / shape / epilogue is not eligible (caller falls through to the FMA kernel)
 static int* g_tc_err = nullptr;
 static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
-    static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("B200TTS_NO_TC"); enabled = (e && atoi(e)) ? 0 : 1; }
-    if (!enabled || !L.allow_tc || !L.w_tc || L.ups != 1 || a.Tq < 128) return -1;
-    if (a.act == ACT_LOGCLAMP || (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2))) return -1;
-    const int rows_pad = (tc::TT + (L.K - 1) * L.dil + 7) / 8 * 8;
-    if (tc::NSLAB * rows_pad > tc::MAXIT * tc::PGROUP) return -1;
-    const size_t smem = tc::smem_bytes(L.tc_n, rows_pad);
-    if (smem > 227 * 1024) return -1;
+    static int enabled = -1, v2_enabled = -1, num_sms = 0;
+    if (enabled < 0) {
+        const char* e = getenv("B200TTS_NO_TC");
+        enabled = (e && atoi(e)) ? 0 : 1;
+        const char* e2 = getenv("B200TTS_NO_TC2");
+        v2_enabled = (e2 && atoi(e2)) ? 0 : 1;
+    }
+    if (!enabled || !L.allow_tc || !L.w_tc || a.Tq < 128) return -1;
+    if (a.act == ACT_LOGCLAMP || a.act == ACT_TANH || (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2 | EPI_GATE))) return -1;
     static bool init_done = false;
     if (!init_done) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc2::conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaMalloc((void**)&g_tc_err, sizeof(int)));
         B200_CUDA_OK(cudaMemset(g_tc_err, 0, sizeof(int)));
+        int dev = 0;
+        B200_CUDA_OK(cudaGetDevice(&dev));
+        B200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         init_done = true;
     }
+    const int rows_pad = (tc::TT + (L.K - 1) * L.dil + 7) / 8 * 8;
+    // ---- persistent kernel (needs 16-byte aligned activation rows for its cp.async staging; no input mask)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) && (a.x_cs % 4 == 0) && (a.x_bs % 4 == 0);
+    const int n_rtiles = (L.Rows + L.tc_n - 1) / L.tc_n;
+    const bool persistent_ok = v2_enabled && aligned && !a.xmask &&
+                               (L.ups == 1 || (!a.res && !(a.flags & EPI_ACCUM) && !a.ymask && !a.cond));
+    if (persistent_ok && L.tc_n == 128 && tc3::smem_bytes3(rows_pad, rows_pad + 4) <= 227 * 1024) {
+        // third generation: M = rows (128, zero padded), N = 256 time steps
+        tc3::Tc3Args t;
+        memset(&t, 0, sizeof(t));
+        t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin; t.in_slope = a.in_slope;
+        t.w = L.w_tc; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
+        t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = 128;
+        t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout; t.ups = L.ups; t.Tq = a.Tq;
+        t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
+        t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;
+        t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
+        t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
+        t.rows_pad = rows_pad; t.raw_w = rows_pad + 4;
+        t.B = io.B; t.n_ttiles = (a.Tq + tc3::TT2 - 1) / tc3::TT2; t.n_rtiles = n_rtiles;
+        t.err = g_tc_err;
+        const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
+        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+        tc3::conv1d_tc3_kernel<<<grid, tc3::NTHREADS2, tc3::smem_bytes3(rows_pad, rows_pad + 4), st>>>(t);
+        count_launch();
+        B200_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    const size_t smem2 = tc2::smem_bytes2(L.tc_n, rows_pad, rows_pad + 4);
+    if (persistent_ok && L.tc_n < 128 && smem2 <= 227 * 1024) {
+        tc2::Tc2Args t;
+        memset(&t, 0, sizeof(t));
+        t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin; t.in_slope = a.in_slope;
+        t.w = L.w_tc; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
+        t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = L.tc_n;
+        t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout; t.ups = L.ups; t.Tq = a.Tq;
+        t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
+        t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;
+        t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
+        t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
+        t.rows_pad = rows_pad; t.raw_w = rows_pad + 4;
+        t.B = io.B; t.n_ttiles = (a.Tq + tc2::TT2 - 1) / tc2::TT2; t.n_rtiles = n_rtiles;
+        t.err = g_tc_err; t.tg = tc2::taps_per_slot(L.tc_n);
+        const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
+        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+        tc2::conv1d_tc2_kernel<<<grid, tc2::NTHREADS2, smem2, st>>>(t);
+        count_launch();
+        B200_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    // ---- first-generation kernel (one tile per CTA; any alignment, optional input mask)
+    if (L.ups != 1) return -1;
+    if (tc::NSLAB * rows_pad > tc::MAXIT * tc::PGROUP) return -1;
+    const size_t smem = tc::smem_bytes(L.tc_n, rows_pad);
+    if (smem > 227 * 1024) return -1;
     tc::TcArgs t;
     memset(&t, 0, sizeof(t));
     t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin;
@@ -549,7 +615,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
     t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
     t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
     t.rows_pad = rows_pad; t.err = g_tc_err;
-    dim3 grid((a.Tq + tc::TT - 1) / tc::TT, L.Rows / L.tc_n, io.B);
+    dim3 grid((a.Tq + tc::TT - 1) / tc::TT, n_rtiles, io.B);
     if (grid.y > 65535 || grid.z > 65535) return -1;
     tc::conv1d_tc_kernel<<<grid, tc::NTHREADS, smem, st>>>(t);
     count_launch();

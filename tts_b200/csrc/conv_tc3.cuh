@@ -1,0 +1,384 @@
+// Persistent tcgen05 3xTF32 conv1d, third generation: M = output rows (weights are the A operand), N = 256 time
+// steps (the activation window is the B operand), D[row, t] in TMEM (128 lanes x 256 columns, double buffered).
+//
+// Why this orientation: measured on B200 (profiles/r01_tc_notes.md) an SS-mode tcgen05.mma with M = 128 costs ~135
+// cycles whatever N is -- the 128-row A operand streams from shared memory at about one 32-byte row per clock.  With
+// the time axis as N = 256 each instruction carries 128 x 256 x 8 MACs in those ~128 cycles instead of 128 x N_cout x 8.
+// The activation tile keeps the row-shift property (rows are 16 B apart), so tap k is still just a descriptor
+// start-address offset of k*dil rows -- now on the B operand.
+//
+//   warps 4-7        producers : cp.async raw [8 ch][time] windows (4-deep ring) -> leaky-ReLU + hi/lo split -> K-major slabs
+//   warp  8          loader    : per-tap weight blocks {hi,lo}[2 slabs][128 rows][4] by cp.async.bulk (10-deep ring)
+//   warp  9          MMA       : one lane issues 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per tap and chunk, commits to mbarriers
+//   warps 0-3,10-13  epilogue  : lane = output row, columns = time: TMEM -> registers -> float4 global stores (two halves
+//                                of the 256 columns), residual / accumulate loads as float4 with an order-enforced prefetch
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_tc.cuh"   // descriptor / barrier helpers
+
+namespace b200tts {
+namespace tc3 {
+
+using namespace tc;       // smem_u32, mbar_*, make_desc, make_idesc, mma_tf32, mma_commit, tmem_ld16, fences
+
+constexpr int TT2 = 256;          // time steps per tile = MMA N
+constexpr int MROWS = 128;        // output rows per tile = MMA M (weight rows are zero padded up to it)
+constexpr int KC2 = 8;            // input channels per chunk (2 slabs, one MMA k-step)
+constexpr int NRAW = 4;           // raw (cp.async) ring depth
+constexpr int NA2 = 3;            // transformed activation stages
+constexpr int NB2 = 10;           // weight ring depth (one 8 KB tap block per slot)
+constexpr int NTHREADS2 = 448;    // warps 0-3 + 10-13 epilogue, 4-7 producers, 8 loader, 9 MMA
+constexpr int NPROD = 128;
+
+struct Tc3Args {
+    const float* x; long long x_bs; int x_cs; int Tin;
+    float in_slope;
+    const float* w;            // packed [row_tile][chunk][tap]{hi[2][128][4], lo[2][128][4]}
+    const float* bias;
+    const float* cond; long long cond_bs;
+    int Cin, K, dil, pad, Rows, N;
+    float* y; long long y_bs; int y_cs; int Tout;
+    int ups;                   // 1, or the polyphase factor of a transposed conv (row r -> channel r/ups, phase r%ups)
+    int Tq;                    // GEMM columns in time (= Tout for ups == 1)
+    const float* res; long long res_bs; int res_cs;
+    const float* ymask; long long ymask_bs;
+    float scale; float post_div; int relu; int accum; int mask_post;
+    int rows_pad;              // slab rows  (TT2 + halo, multiple of 8)
+    int raw_w;                 // raw row width in floats (rows_pad + 4, multiple of 4)
+    int B, n_ttiles, n_rtiles;
+    int* err;
+    unsigned long long* trace;  // optional [grid][32] globaltimer stamps (debug)
+};
+
+static inline size_t smem_bytes3(int rows_pad, int raw_w) {
+    return (size_t)NRAW * KC2 * raw_w * 4 + (size_t)NA2 * (4 * rows_pad * 16) + (size_t)NB2 * (4 * MROWS * 16) + 512;
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+#define TC3_STAMP(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime(); } while (0)
+
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ROWS = a.rows_pad, RAWW = a.raw_w, K = a.K;
+    const uint32_t rawStage = (uint32_t)KC2 * RAWW * 4;
+    const uint32_t slabA = (uint32_t)ROWS * 16, stageA = 4 * slabA;     // hi[2] + lo[2]
+    const uint32_t slabB = (uint32_t)MROWS * 16, stageB = 4 * slabB;   // one tap block: {hi,lo}[2 slabs][128 rows][16 B]
+    unsigned char* smRaw = smem;
+    unsigned char* smA = smRaw + NRAW * rawStage;
+    unsigned char* smB = smA + NA2 * stageA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + NB2 * stageB);
+    const int A_FULL = 0, A_EMPTY = NA2, B_FULL = 2 * NA2, B_EMPTY = 2 * NA2 + NB2, ACC_FULL = 2 * NA2 + 2 * NB2,
+              ACC_EMPTY = ACC_FULL + 2, NBARS = ACC_EMPTY + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    const int nchunks = (a.Cin + KC2 - 1) / KC2;
+    const int tiles_total = a.B * a.n_rtiles * a.n_ttiles;
+    const int my_tiles = (tiles_total > (int)blockIdx.x) ? (tiles_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t acc_cols = (uint32_t)TT2;                     // per accumulator buffer
+    const uint32_t ncols = 512;
+
+    if (tid == 0) {
+        for (int i = 0; i < NA2; ++i) { mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < NB2; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) TC3_STAMP(0);
+
+    auto decode = [&](int it, int& b, int& rt, int& q0) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int tt = tile % a.n_ttiles, rest = tile / a.n_ttiles;
+        rt = rest % a.n_rtiles;
+        b = rest / a.n_rtiles;
+        q0 = tt * TT2;
+    };
+
+    if (warp >= 4 && warp < 8) {
+        // ============================================================ producers
+        const int ptid = tid - 128;
+        const int total = my_tiles * nchunks;
+        const int vec_per_row = RAWW / 4;
+        const int nvec = KC2 * vec_per_row;
+        const float slope = a.in_slope;
+        bool ok = true;
+        // per-thread work items are the same for every chunk: decode them once (no divisions in the loop)
+        constexpr int MAXV = 6, MAXI = 5;          // ceil(8*81/128), ceil(2*320/128)
+        int v_off[MAXV], v_ch[MAXV], v_t[MAXV];    // raw smem float offset, channel in chunk, time offset from `tal`
+#pragma unroll
+        for (int e = 0; e < MAXV; ++e) {
+            const int v = ptid + e * NPROD;
+            const int ch = v / vec_per_row, j = v - ch * vec_per_row;
+            v_ch[e] = (v < nvec) ? ch : -1;
+            v_t[e] = 4 * j;
+            v_off[e] = ch * RAWW + 4 * j;
+        }
+        int i_raw[MAXI], i_dst[MAXI];              // raw float offset of channel 0 of the slab, slab byte offset
+#pragma unroll
+        for (int e = 0; e < MAXI; ++e) {
+            const int idx = ptid + e * NPROD;
+            const int sl = idx / ROWS, r = idx - sl * ROWS;
+            i_raw[e] = (idx < 2 * ROWS) ? (4 * sl) * RAWW + r : -1;
+            i_dst[e] = (int)(sl * slabA) + r * 16;
+        }
+        auto issue = [&](int g) {
+            if (g < total) {
+                const int it = g / nchunks, c = g - it * nchunks;
+                int b, rt, q0;
+                decode(it, b, rt, q0);
+                const int tal = ((q0 - a.pad) & ~3);                     // 16-byte aligned window start (may be < 0)
+                const float* xb = a.x + (long long)b * a.x_bs;
+                const uint32_t dst0 = smem_u32(smRaw + (g % NRAW) * rawStage);
+#pragma unroll
+                for (int e = 0; e < MAXV; ++e) {
+                    if (v_ch[e] < 0) continue;
+                    const int t = tal + v_t[e];
+                    const int cg = c * KC2 + v_ch[e];
+                    // t is a multiple of 4, so a vector is either wholly before the sequence start (zero fill),
+                    // wholly inside, or cut by its end (partial source size, rest zero-filled by the hardware)
+                    int nb = 0;
+                    if (cg < a.Cin && t >= 0) nb = 4 * max(0, min(4, a.Tin - t));
+                    const int tsafe = (t >= 0 && t < a.Tin) ? t : 0;
+                    const float* src = xb + (long long)(cg < a.Cin ? cg : 0) * a.x_cs + tsafe;
+                    cp_async16_zfill(dst0 + (uint32_t)v_off[e] * 4u, src, (uint32_t)nb);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int g = 0; g < NRAW - 1; ++g) issue(g);
+        for (int g = 0; g < total && ok; ++g) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(NRAW - 2) : "memory");
+            named_bar_sync(1, NPROD);                                     // everyone's copies of chunk g have landed
+            issue(g + NRAW - 1);                                          // refills the stage transformed last iteration
+            const int as = g % NA2;
+            if (g >= NA2) ok = mbar_wait(BAR(A_EMPTY + as), ((g / NA2) - 1) & 1, a.err);
+            if (!ok) break;
+            const int it = g / nchunks;
+            int b, rt, q0;
+            decode(it, b, rt, q0);
+            const int tin0 = q0 - a.pad, off = tin0 - (tin0 & ~3);
+            const float* raw = reinterpret_cast<const float*>(smRaw + (g % NRAW) * rawStage) + off;
+            unsigned char* base = smA + as * stageA;
+            float u[MAXI][4];
+#pragma unroll
+            for (int e = 0; e < MAXI; ++e) {           // all shared loads first ...
+                const int o = i_raw[e] < 0 ? 0 : i_raw[e];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) u[e][i] = raw[o + i * RAWW];
+            }
+#pragma unroll
+            for (int e = 0; e < MAXI; ++e) {           // ... then prologue, hi/lo split and the two 16-byte stores
+                if (i_raw[e] < 0) continue;
+                float4 hi, lo;
+                float* ph = &hi.x; float* pl = &lo.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float w_ = u[e][i];
+                    w_ = w_ > 0.f ? w_ : w_ * slope;
+                    const float h = __uint_as_float(__float_as_uint(w_) & 0xFFFFE000u);
+                    ph[i] = h;
+                    pl[i] = w_ - h;
+                }
+                *reinterpret_cast<float4*>(base + i_dst[e]) = hi;
+                *reinterpret_cast<float4*>(base + 2 * slabA + i_dst[e]) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(BAR(A_FULL + as));
+            if (ptid == 0) { if (g == 0) TC3_STAMP(1); if (g == nchunks - 1) TC3_STAMP(2); if (g == 2 * nchunks - 1) TC3_STAMP(3); if (g == 4 * nchunks - 1) TC3_STAMP(4); }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (ptid == 0) TC3_STAMP(5);
+    } else if (warp == 8) {
+        // ============================================================ weight loader
+        if (lane == 0) {
+            bool ok = true;
+            int gi = 0;
+            const int total = nchunks * K;                                 // tap blocks per tile (contiguous in memory)
+            for (int it = 0; it < my_tiles && ok; ++it) {
+                int b, rt, q0;
+                decode(it, b, rt, q0);
+                const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.w) + (size_t)rt * total * stageB;
+                for (int j = 0; j < total && ok; ++j, ++gi) {
+                    const int st = gi % NB2;
+                    if (gi >= NB2) ok = mbar_wait(BAR(B_EMPTY + st), ((gi / NB2) - 1) & 1, a.err);
+                    if (!ok) break;
+                    mbar_expect_tx(BAR(B_FULL + st), stageB);
+                    bulk_g2s(smem_u32(smB + st * stageB), wsrc + (size_t)j * stageB, stageB, BAR(B_FULL + st));
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            // M = 128 rows (weights), N = 256 time steps
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TT2 >> 3) << 17) | ((uint32_t)(MROWS >> 4) << 24);
+            bool ok = true;
+            int g = 0, gi = 0;
+            for (int it = 0; it < my_tiles && ok; ++it) {
+                const int buf = it & 1;
+                if (it >= 2) ok = mbar_wait(BAR(ACC_EMPTY + buf), ((it >> 1) - 1) & 1, a.err);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + (uint32_t)buf * acc_cols;
+                for (int c = 0; c < nchunks && ok; ++c, ++g) {
+                    const int sa = g % NA2;
+                    ok = mbar_wait(BAR(A_FULL + sa), (g / NA2) & 1, a.err);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(smA + sa * stageA);
+                    // descriptors differ only in the 14-bit start-address field: build once, then add rows (16 B each)
+                    const uint64_t x_hi0 = make_desc(abase, slabA), x_lo0 = make_desc(abase + 2 * slabA, slabA);
+                    for (int k = 0; k < K && ok; ++k, ++gi) {
+                        const int sb = gi % NB2;
+                        ok = mbar_wait(BAR(B_FULL + sb), (gi / NB2) & 1, a.err);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint32_t bbase = smem_u32(smB + sb * stageB);
+                        const uint64_t w_hi = make_desc(bbase, slabB);
+                        const uint64_t w_lo = w_hi + (uint64_t)((2 * slabB) >> 4);
+                        const uint64_t xrow = (uint64_t)(k * a.dil);
+                        mma_tf32(dcol, w_hi, x_lo0 + xrow, idesc, (c == 0 && k == 0) ? 0u : 1u);   // small terms first
+                        mma_tf32(dcol, w_lo, x_hi0 + xrow, idesc, 1u);
+                        mma_tf32(dcol, w_hi, x_hi0 + xrow, idesc, 1u);
+                        mma_commit(BAR(B_EMPTY + sb));
+                    }
+                    if (ok) mma_commit(BAR(A_EMPTY + sa));
+                }
+                if (ok) mma_commit(BAR(ACC_FULL + buf));
+                if (it == 0) TC3_STAMP(8); if (it == 1) TC3_STAMP(9); if (it == 3) TC3_STAMP(10);
+            }
+            TC3_STAMP(11);
+        }
+        __syncwarp();
+    } else {
+        // ============================================================ epilogue (lane = output row, columns = time)
+        bool ok = true;
+        const int ups = a.ups;
+        const int lq = warp & 3;                     // TMEM lane quarter this warp may access
+        const int half = (warp >= 10) ? 1 : 0;       // warps 0-3: columns [0,128), warps 10-13: [128,256)
+        for (int it = 0; it < my_tiles && ok; ++it) {
+            const int buf = it & 1;
+            int b, rt, q0;
+            decode(it, b, rt, q0);
+            ok = mbar_wait(BAR(ACC_FULL + buf), (it >> 1) & 1, a.err);
+            if (!ok) break;
+            tc_fence_after();
+            if (tid == 0) { if (it == 0) TC3_STAMP(16); if (it == 1) TC3_STAMP(18); if (it == 3) TC3_STAMP(20); }
+            const int r = rt * MROWS + lq * 32 + lane;             // GEMM row of this lane
+            const bool rok = r < a.Rows;
+            const int rc = rok ? r : a.Rows - 1;
+            const uint32_t dbase = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 128);
+            const int qb = q0 + half * 128;
+            float bias = a.bias[rc];
+            if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + rc);
+            if (ups == 1) {
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;
+                const float* rrow = a.res ? a.res + (long long)b * a.res_bs + (long long)rc * a.res_cs : nullptr;
+                const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
+                const bool vec_ok = ((a.y_cs & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
+                                    ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
+                                    (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+                float rv[16], ov[16];
+                // order-enforced software pipeline: the (volatile) loads of group j+1 are issued before the (volatile)
+                // TMEM load of group j.  float4 per lane along time (each lane owns one output row).
+                auto prefetch = [&](int cg, float* r_, float* o_) {
+                    const int q = qb + cg;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int qq = q + 4 * j;
+                        if (vec_ok && qq + 3 < a.Tout) {
+                            if (rrow) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rrow + qq));
+                            if (a.accum) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int qe = min(qq + e, a.Tout - 1);
+                                if (rrow) asm volatile("ld.global.f32 %0, [%1];" : "=f"(r_[4 * j + e]) : "l"(rrow + qe));
+                                if (a.accum) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
+                            }
+                        }
+                    }
+                };
+                if (rok) prefetch(0, rv, ov);
+                for (int cg = 0; cg < 128; cg += 16) {
+                    float v[16], rn[16], on[16];
+                    if (rok && cg + 16 < 128) prefetch(cg + 16, rn, on);
+                    tmem_ld16(dbase + (uint32_t)cg, v);
+                    const int q = qb + cg;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float u = v[i] + bias;
+                        if (a.relu) u = fmaxf(u, 0.f);
+                        if (a.res) u += rv[i];
+                        u *= a.scale;
+                        if (a.accum) u += ov[i];
+                        if (a.post_div != 1.f) u = u / a.post_div;
+                        if (a.mask_post) u *= __ldg(mrow + min(q + i, a.Tout - 1));
+                        v[i] = u;
+                    }
+                    if (rok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int qq = q + 4 * j;
+                            if (vec_ok && qq + 3 < a.Tout) {
+                                *reinterpret_cast<float4*>(yrow + qq) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = v[4 * j + e];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { rv[i] = rn[i]; ov[i] = on[i]; }
+                }
+            } else {
+                // polyphase store: row r = co*ups + ph, column q -> y[co][q*ups + ph]; a warp's 32 lanes cover whole
+                // groups of `ups` phases, i.e. contiguous runs of `ups` output samples per channel
+                const int co = rc / ups, ph = rc - co * ups;
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs + ph;
+                for (int cg = 0; cg < 128; cg += 16) {
+                    float v[16];
+                    tmem_ld16(dbase + (uint32_t)cg, v);
+                    if (!rok) continue;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int q = qb + cg + i;
+                        float u = v[i] + bias;
+                        if (a.relu) u = fmaxf(u, 0.f);
+                        const long long t = (long long)q * ups;
+                        if (q < a.Tq && t + ph < a.Tout) yrow[t] = u;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(ACC_EMPTY + buf));
+            if (tid == 0) { if (it == 0) TC3_STAMP(17); if (it == 1) TC3_STAMP(19); if (it == 3) TC3_STAMP(21); }
+        }
+        if (tid == 0) TC3_STAMP(22);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace tc3
+}  // namespace b200tts

@@ -65,6 +65,7 @@ int Hifigan::init(const b200tts_hifigan_config& cfg, const float* const* w, int 
     rc = pack_conv(conv_post, w[i], w[i + 1], c.out_channels, ch, 7, 1, 3);
     // the MRF / pre convs carry ~97% of the FLOPs: run them on the tcgen05 3xTF32 kernel
     conv_pre.allow_tc = true;
+    for (auto& l : ups) l.allow_tc = true;
     for (auto& v : rb_c1) for (auto& l : v) l.allow_tc = true;
     for (auto& v : rb_c2) for (auto& l : v) l.allow_tc = true;
     return rc;
