@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -61,9 +61,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: call at the start of the timed region."""
+        return len(self.rows)
+
+    def stop(self, first=0):
         if self.proc is not None:
             self.proc.terminate()
+        rows = self.rows[first:] or self.rows[-1:]
+        self.rows = rows
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -94,8 +100,8 @@ def cpu_reference_samples_per_s(nbatch, steps=1, warmup=0, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vits_oracle as O
     from dataclasses import asdict
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores (torchrun exports OMP_NUM_THREADS=1; override it at run time)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     model = build_model()
     sd = model.state_dict()
     args = asdict(model.args)
@@ -192,13 +198,16 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the sampler process attaches to the GPU when it starts (a tens-of-ms stall): start it before the warm-up and
+    # only keep the samples taken inside the timed region
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
 
     # ---------------- timed region 1: device-resident inputs
-    sampler = ClockSampler(local)
-    sampler.start()
+    first_sample = sampler.mark()
     launches0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_ev = []
@@ -217,12 +226,15 @@ def run_cuda(args):
         frames_padded += out["y_mask"].shape[0] * out["y_mask"].shape[-1]
     barrier()
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(first_sample)
     t_resident = sum(s.elapsed_time(e) for s, e in ev) / 1e3
     dec_ms = sum(a.elapsed_time(b) for n, a, b in stage_ev if n == "waveform_decoder")
     stage_ms = {}
     for n, a, b in stage_ev:
         stage_ms[n] = stage_ms.get(n, 0.0) + a.elapsed_time(b)
+    if os.environ.get("BENCH_DEBUG") and rank == 0:
+        print("per-step ms:", [round(s.elapsed_time(e), 2) for s, e in ev], file=sys.stderr)
+        print("per-stage:", [(n, round(a.elapsed_time(b), 2)) for n, a, b in stage_ev], file=sys.stderr)
 
     # ---------------- timed region 2: end to end from pinned host buffers
     for _ in range(2):

@@ -535,7 +535,8 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         v2_enabled = (e2 && atoi(e2)) ? 0 : 1;
     }
     if (!enabled || !L.allow_tc || !L.w_tc || a.Tq < 128) return -1;
-    if (a.act == ACT_LOGCLAMP || a.act == ACT_TANH || (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2 | EPI_GATE))) return -1;
+    if (a.act == ACT_LOGCLAMP || a.act == ACT_TANH) return -1;
+    const bool needs_v3 = (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2 | EPI_GATE)) != 0;
     static bool init_done = false;
     if (!init_done) {
         B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -566,6 +567,10 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;
         t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
         t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
+        t.mask_pre = (a.flags & EPI_MASK_PRE) ? 1 : 0;
+        t.gate = (a.flags & EPI_GATE) ? 1 : 0;
+        t.split = (a.flags & EPI_SPLIT) ? a.split : 0;
+        t.y2 = a.y2; t.y2_bs = a.y2_bs; t.y2_cs = a.y2_cs; t.accum2 = (a.flags & EPI_ACCUM2) ? 1 : 0;
         t.rows_pad = rows_pad; t.raw_w = rows_pad + 4;
         t.B = io.B; t.n_ttiles = (a.Tq + tc3::TT2 - 1) / tc3::TT2; t.n_rtiles = n_rtiles;
         t.err = g_tc_err;
@@ -576,6 +581,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         B200_CUDA_OK(cudaGetLastError());
         return 0;
     }
+    if (needs_v3) return -1;   // only the third-generation kernel implements gate / split / pre-mask epilogues
     const size_t smem2 = tc2::smem_bytes2(L.tc_n, rows_pad, rows_pad + 4);
     if (persistent_ok && L.tc_n < 128 && smem2 <= 227 * 1024) {
         tc2::Tc2Args t;
@@ -651,6 +657,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     B200_REQUIRE(!(io.ymask && L.ups > 1), "launch_conv: output mask with an upsampling layer is not supported");
     if (a.flags & EPI_GATE) {
         B200_REQUIRE(L.ups == 1 && !io.res && a.act == ACT_NONE, "launch_conv: gate epilogue takes no other options");
+        if (int rc = try_launch_tc(L, io, a, st); rc != -1) return rc;
         return launch_cic<KEPI_GATE>(a, L.co_tile, io.B, L.RowsPad, st);
     }
     if (a.act == ACT_TANH) {

@@ -45,6 +45,10 @@ struct Tc3Args {
     const float* res; long long res_bs; int res_cs;
     const float* ymask; long long ymask_bs;
     float scale; float post_div; int relu; int accum; int mask_post;
+    int mask_pre;              // multiply by ymask before the residual / accumulate (coupling `post`)
+    int gate;                  // rows are (tanh, sigmoid) pairs: out[r/2] = tanh(v[2p]) * sigmoid(v[2p+1])  (WaveNet)
+    int split;                 // > 0: rows < split -> y (accumulate, mask); rows >= split -> y2 (accumulate iff accum2)
+    float* y2; long long y2_bs; int y2_cs; int accum2;
     int rows_pad;              // slab rows  (TT2 + halo, multiple of 8)
     int raw_w;                 // raw row width in floats (rows_pad + 4, multiple of 4)
     int B, n_ttiles, n_rtiles;
@@ -287,11 +291,45 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
             const int qb = q0 + half * 128;
             float bias = a.bias[rc];
             if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + rc);
-            if (ups == 1) {
+            if (a.gate) {
+                // WaveNet gate (wavenet.py:6-13): even lane = tanh argument, odd lane = sigmoid argument of row r/2
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)(rc >> 1) * a.y_cs;
+                const bool vec_ok = ((a.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0);
+                const bool even = (lane & 1) == 0;
+                for (int cg = 0; cg < 128; cg += 16) {
+                    float v[16];
+                    tmem_ld16(dbase + (uint32_t)cg, v);
+                    const int q = qb + cg;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float u = v[i] + bias;
+                        const float act = even ? tanhf(u) : 1.f / (1.f + expf(-u));
+                        const float other = __shfl_xor_sync(0xffffffffu, act, 1);
+                        v[i] = act * other;
+                    }
+                    if (rok && even) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int qq = q + 4 * j;
+                            if (vec_ok && qq + 3 < a.Tout) *reinterpret_cast<float4*>(yrow + qq) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = v[4 * j + e];
+                            }
+                        }
+                    }
+                }
+            } else if (ups == 1) {
                 float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;
+                bool acc_r = a.accum != 0, mpost_r = a.mask_post != 0;
+                if (a.split > 0) {          // WaveNet res/skip rows (wavenet.py:108-113)
+                    if (rc < a.split) { acc_r = true; mpost_r = true; }
+                    else { yrow = a.y2 + (long long)b * a.y2_bs + (long long)(rc - a.split) * a.y2_cs; acc_r = a.accum2 != 0; mpost_r = false; }
+                }
                 const float* rrow = a.res ? a.res + (long long)b * a.res_bs + (long long)rc * a.res_cs : nullptr;
                 const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
-                const bool vec_ok = ((a.y_cs & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
+                const int ycs_eff = (a.split > 0 && rc >= a.split) ? a.y2_cs : a.y_cs;
+                const bool vec_ok = ((ycs_eff & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
                                     ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
                                     (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
                 float rv[16], ov[16];
@@ -304,13 +342,13 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
                         const int qq = q + 4 * j;
                         if (vec_ok && qq + 3 < a.Tout) {
                             if (rrow) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rrow + qq));
-                            if (a.accum) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
+                            if (acc_r) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int qe = min(qq + e, a.Tout - 1);
                                 if (rrow) asm volatile("ld.global.f32 %0, [%1];" : "=f"(r_[4 * j + e]) : "l"(rrow + qe));
-                                if (a.accum) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
+                                if (acc_r) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
                             }
                         }
                     }
@@ -325,11 +363,13 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
                     for (int i = 0; i < 16; ++i) {
                         float u = v[i] + bias;
                         if (a.relu) u = fmaxf(u, 0.f);
+                        const float mk = mrow ? __ldg(mrow + min(q + i, a.Tout - 1)) : 1.f;
+                        if (a.mask_pre) u *= mk;
                         if (a.res) u += rv[i];
                         u *= a.scale;
-                        if (a.accum) u += ov[i];
+                        if (acc_r) u += ov[i];
                         if (a.post_div != 1.f) u = u / a.post_div;
-                        if (a.mask_post) u *= __ldg(mrow + min(q + i, a.Tout - 1));
+                        if (mpost_r) u *= mk;
                         v[i] = u;
                     }
                     if (rok) {

@@ -170,9 +170,14 @@ class ResidualCouplingBlocks(EngineModule):
         _lib.require_cuda(x, "x")
         if self.cond_channels > 0 and g is None:
             raise ValueError("tts_b200.ResidualCouplingBlocks: cond_channels > 0 but g is None")
-        z = x.to(torch.float32).contiguous().clone()
-        b, c, t = z.shape
-        mask = x_mask.to(torch.float32).expand(b, 1, t).contiguous()
+        b, c, t_in = x.shape
+        # everything in the flow is re-masked after each layer, so zero-masked extra frames are exact; padding T to
+        # a multiple of 4 keeps activation rows 16-byte aligned for the tensor-core kernel's cp.async staging
+        t = (t_in + 3) // 4 * 4
+        z = torch.zeros((b, c, t), dtype=torch.float32, device=x.device)
+        z[:, :, :t_in] = x
+        mask = torch.zeros((b, 1, t), dtype=torch.float32, device=x.device)
+        mask[:, :, :t_in] = x_mask
         gl = None if self.cond_channels == 0 else g.to(torch.float32).contiguous()
         h = self.handle(z.device)
         L = _lib.lib()
@@ -181,7 +186,7 @@ class ResidualCouplingBlocks(EngineModule):
             rc = L.b200tts_flow_reverse(h, _lib.ptr(z), _lib.ptr(mask), _lib.ptr(gl), b, t, _lib.ptr(ws),
                                         ctypes.c_size_t(ws.numel()), _lib.stream_ptr(z.device))
         _lib.check(rc, "flow_reverse")
-        return z
+        return z if t == t_in else z[:, :, :t_in].contiguous()
 
 
 class PosteriorEncoder(nn.Module):
