@@ -32,6 +32,10 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc));
 }
 
+__device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 struct MasArgs {
     const float* value; const float* mask; const int* t_x; const int* t_y;
     int B, Tx, Ty, YT, W;     // W = ceil(Tx/32) words per direction row
@@ -182,6 +186,179 @@ __global__ void __launch_bounds__(MAS_NT) mas_kernel(const MasArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ lean kernel for Tx <= 256 (one thread per text position)
+// Same semantics as mas_kernel, ~3x fewer instructions per DP step: the stored column lives in a register, the left
+// neighbour comes from __shfl_up (only warp-boundary values go through shared memory), band limits are warp-uniform,
+// and value tiles are staged transposed ([yy][x], pitch odd mod 32) so both the 4-byte cp.async writes and the
+// per-step reads are bank-conflict free.
+constexpr int MAS2_YT = 16;
+
+template <bool HAS_MASK, bool DIRS_SMEM>
+__global__ void __launch_bounds__(MAS_NT) mas_kernel2(const MasArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Tx = a.Tx, Ty = a.Ty, W = a.W;
+    constexpr int YT = MAS2_YT, NW = MAS_NT / 32;
+    const int TxP = (Tx | 31) + 2;                 // pitch == 1 (mod 32)
+    int tx = min(max(a.t_x[b], 0), Tx), ty = min(max(a.t_y[b], 0), Ty);
+    constexpr bool has_mask = HAS_MASK;
+    float* tileV = reinterpret_cast<float*>(smem_raw);                    // [2][YT][TxP]
+    float* tileM = tileV + 2 * YT * TxP;                                  // [2][YT][TxP] or empty
+    float* bound = tileM + (has_mask ? 2 * YT * TxP : 0);                 // [2][NW]
+    int* idxs = reinterpret_cast<int*>(bound + 2 * NW);                   // [Ty]
+    unsigned* dirs_s = reinterpret_cast<unsigned*>(idxs + Ty);             // [Ty][W] when DIRS_SMEM
+    unsigned* dirs_g = a.dirs_global + (size_t)b * Ty * W;
+    const float* vb = a.value + (size_t)b * Tx * Ty;
+    const float* mbp = has_mask ? a.mask + (size_t)b * Tx * Ty : nullptr;
+
+    // loader mapping: lane -> (yy, row-in-group); a warp covers 32/YT rows per iteration
+    const int l_yy = lane % YT, l_xs = lane / YT;
+    constexpr int RPI = 32 / YT;                                          // rows per warp iteration
+    auto load_tile = [&](int tile, int buf) {
+        const int y = tile * YT + l_yy;
+        float* dv = tileV + buf * YT * TxP + l_yy * TxP;
+        float* dm = tileM + buf * YT * TxP + l_yy * TxP;
+        if (y < ty) {
+            for (int x = warp * RPI + l_xs; x < Tx; x += NW * RPI) {
+                cp_async4(dv + x, vb + (size_t)x * Ty + y);
+                if (has_mask) cp_async4(dm + x, mbp + (size_t)x * Ty + y);
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (tid < 2 * NW) bound[tid] = 0.f;
+
+    const int x = tid;
+    const bool xin = x < Tx;
+    // per-thread invariants of the band test  max(0, tx+y-ty) <= x < min(tx, y+1):
+    //   x < tx (constant), x <= y, x - tx + ty >= y
+    const bool x_lt_tx = x < tx;
+    const int c1 = x - tx + ty;
+    const bool is_x0 = (x == 0);
+    const float neg = a.max_neg;
+    float vc = 0.f;                                                       // stored[x, y-1]
+    float* bnd_w = bound + warp;                                          // this warp's slot (written by lane 31)
+    const float* bnd_r = bound + (warp > 0 ? warp - 1 : 0);               // left warp's slot (read by lane 0)
+    const bool rd_bound = (lane == 0) && (warp > 0);
+    const bool wr_bound = (lane == 31);
+    const bool wr_dir = (lane == 0) && (warp < W);
+    const unsigned a_bnd_w = (unsigned)__cvta_generic_to_shared(bnd_w);
+    const unsigned a_bnd_r = (unsigned)__cvta_generic_to_shared(bnd_r);
+    const unsigned a_dirs0 = (unsigned)__cvta_generic_to_shared(dirs_s + warp);
+    const int ntiles = (ty + YT - 1) / YT;
+    if (ntiles > 0) load_tile(0, 0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) { load_tile(tile + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // raw 32-bit shared addresses kept in registers (the generic-pointer form recomputed the window base per step)
+        unsigned a_tv = (unsigned)__cvta_generic_to_shared(tileV + buf * YT * TxP + (xin ? x : 0));
+        unsigned a_tm = (unsigned)__cvta_generic_to_shared(tileM + buf * YT * TxP + (xin ? x : 0));
+        const int y0 = tile * YT, ylim = min(YT, ty - y0);
+        unsigned a_dir = a_dirs0 + (unsigned)(y0 * W) * 4u;
+#pragma unroll 1
+        for (int yy = 0; yy < ylim; ++yy) {
+            const int y = y0 + yy;
+            float raw = lds_f32(a_tv);
+            if (HAS_MASK) raw = __fmul_rn(raw, lds_f32(a_tm));
+            float left = __shfl_up_sync(0xffffffffu, vc, 1);
+            const unsigned par = (unsigned)(y & 1) * (NW * 4u);
+            if (rd_bound) left = lds_f32(a_bnd_r + par);
+            // dir[x,y] = (y > 0) && (x != 0) && (x == y || stored[x,y-1] < stored[x-1,y-1])
+            const bool x_eq_y = (x == y);
+            const bool dir = xin && !is_x0 && (y > 0) && (x_eq_y || vc < left);
+            const bool inband = x_lt_tx && (x <= y) && (c1 >= y);
+            const float v_cur = x_eq_y ? neg : vc;
+            const float v_prev = is_x0 ? (y == 0 ? 0.f : neg) : left;
+            const float upd = __fadd_rn(fmaxf(v_cur, v_prev), raw);
+            vc = inband ? upd : (xin ? raw : 0.f);
+            const unsigned word = __ballot_sync(0xffffffffu, dir);
+            if (wr_bound) sts_f32(a_bnd_w + (NW * 4u - par), vc);
+            if (wr_dir) {
+                if (DIRS_SMEM) sts_u32(a_dir, word);
+                else dirs_g[(size_t)y * W + warp] = word;
+            }
+            a_tv += (unsigned)TxP * 4u; a_tm += (unsigned)TxP * 4u; a_dir += (unsigned)W * 4u;
+            __syncthreads();
+        }
+    }
+    const unsigned* dirs = DIRS_SMEM ? dirs_s : dirs_g;
+    __syncthreads();
+    if (warp == 0 && tx > 0) {
+        int index = tx - 1;
+        for (int ytop = ty - 1; ytop >= 0; ytop -= MAS_DEPTH) {
+            unsigned rows[MAS_DEPTH];
+#pragma unroll
+            for (int d = 0; d < MAS_DEPTH; ++d) {
+                const int y = ytop - d;
+                rows[d] = (y >= 1 && lane < W) ? dirs[(size_t)y * W + lane] : 0u;
+            }
+#pragma unroll
+            for (int d = 0; d < MAS_DEPTH; ++d) {
+                const int y = ytop - d;
+                if (y < 0) break;
+                if (lane == 0) idxs[y] = index;
+                if (y >= 1) {
+                    const unsigned word = __shfl_sync(0xffffffffu, rows[d], index >> 5);
+                    index -= (int)((word >> (index & 31)) & 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const bool valid = tx > 0;
+    if (a.path_is_f32) {
+        float* pb = reinterpret_cast<float*>(a.path) + (size_t)b * Tx * Ty;
+        if ((Ty & 3) == 0) {
+            float4* pb4 = reinterpret_cast<float4*>(pb);
+            const int Ty4 = Ty >> 2;
+            for (int xx = warp; xx < Tx; xx += NW)
+                for (int j = lane; j < Ty4; j += 32) {
+                    const int y = j << 2;
+                    float4 o;
+                    o.x = (valid && y + 0 < ty && idxs[y + 0] == xx) ? 1.f : 0.f;
+                    o.y = (valid && y + 1 < ty && idxs[y + 1] == xx) ? 1.f : 0.f;
+                    o.z = (valid && y + 2 < ty && idxs[y + 2] == xx) ? 1.f : 0.f;
+                    o.w = (valid && y + 3 < ty && idxs[y + 3] == xx) ? 1.f : 0.f;
+                    pb4[(size_t)xx * Ty4 + j] = o;
+                }
+        } else {
+            for (size_t i = tid; i < (size_t)Tx * Ty; i += MAS_NT) {
+                const int xx = (int)(i / Ty), y = (int)(i - (size_t)xx * Ty);
+                pb[i] = (valid && y < ty && idxs[y] == xx) ? 1.f : 0.f;
+            }
+        }
+    } else {
+        int* pb = reinterpret_cast<int*>(a.path) + (size_t)b * Tx * Ty;
+        if ((Ty & 3) == 0) {
+            int4* pb4 = reinterpret_cast<int4*>(pb);
+            const int Ty4 = Ty >> 2;
+            for (int xx = warp; xx < Tx; xx += NW)
+                for (int j = lane; j < Ty4; j += 32) {
+                    const int y = j << 2;
+                    int4 o;
+                    o.x = (valid && y + 0 < ty && idxs[y + 0] == xx) ? 1 : 0;
+                    o.y = (valid && y + 1 < ty && idxs[y + 1] == xx) ? 1 : 0;
+                    o.z = (valid && y + 2 < ty && idxs[y + 2] == xx) ? 1 : 0;
+                    o.w = (valid && y + 3 < ty && idxs[y + 3] == xx) ? 1 : 0;
+                    pb4[(size_t)xx * Ty4 + j] = o;
+                }
+        } else {
+            for (size_t i = tid; i < (size_t)Tx * Ty; i += MAS_NT) {
+                const int xx = (int)(i / Ty), y = (int)(i - (size_t)xx * Ty);
+                pb[i] = (valid && y < ty && idxs[y] == xx) ? 1 : 0;
+            }
+        }
+    }
+}
+
+static size_t mas2_smem(int Tx, int Ty, bool has_mask, bool dirs_in_smem) {
+    const int TxP = (Tx | 31) + 2, W = (Tx + 31) / 32;
+    return (size_t)(has_mask ? 4 : 2) * MAS2_YT * TxP * 4 + 2 * (MAS_NT / 32) * 4 + (size_t)Ty * 4 +
+           (dirs_in_smem ? (size_t)Ty * W * 4 : 0) + 16;
+}
+
 struct MasPlan { int YT; int dirs_in_smem; size_t smem; bool ok; };
 
 MasPlan mas_plan(int Tx, int Ty, bool has_mask) {
@@ -212,6 +389,32 @@ int mas_forward(const float* value, const float* mask, const int* t_x, const int
     B200_REQUIRE(B >= 0 && Tx >= 0 && Ty >= 0, "mas: negative size");
     if (B == 0 || Tx == 0 || Ty == 0) return 0;
     B200_REQUIRE(value && t_x && t_y && path, "mas: null pointer");
+    static bool attr2_done = false;
+    if (Tx <= MAS_NT) {     // lean kernel
+        bool dsm = mas2_smem(Tx, Ty, mask != nullptr, true) <= 72 * 1024;
+        const size_t smem2 = mas2_smem(Tx, Ty, mask != nullptr, dsm);
+        if (smem2 <= 200 * 1024 && (dsm || (ws && ws_bytes >= mas_workspace_bytes(B, Tx, Ty)))) {
+            if (!attr2_done) {
+                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr2_done = true;
+            }
+            MasArgs a2;
+            a2.value = value; a2.mask = mask; a2.t_x = t_x; a2.t_y = t_y;
+            a2.B = B; a2.Tx = Tx; a2.Ty = Ty; a2.YT = MAS2_YT; a2.W = (Tx + 31) / 32;
+            a2.path = path; a2.path_is_f32 = path_is_f32;
+            a2.dirs_global = reinterpret_cast<unsigned*>(ws);
+            a2.dirs_in_smem = dsm ? 1 : 0;
+            a2.max_neg = -1e9f;
+            if (mask) { if (dsm) mas_kernel2<true, true><<<B, MAS_NT, smem2, st>>>(a2); else mas_kernel2<true, false><<<B, MAS_NT, smem2, st>>>(a2); }
+            else      { if (dsm) mas_kernel2<false, true><<<B, MAS_NT, smem2, st>>>(a2); else mas_kernel2<false, false><<<B, MAS_NT, smem2, st>>>(a2); }
+            count_launch();
+            B200_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     MasPlan p = mas_plan(Tx, Ty, mask != nullptr);
     B200_REQUIRE(p.ok, "mas: Tx=%d Ty=%d does not fit the shared-memory plan", Tx, Ty);
     B200_REQUIRE(p.dirs_in_smem || (ws && ws_bytes >= mas_workspace_bytes(B, Tx, Ty)), "mas: workspace too small");
