@@ -28,6 +28,9 @@ SR = 22050
 HIFIGAN_FLOP_PER_SAMPLE = 2.402e6      # SURVEY.md section 8d (Cin=192)
 FLOW_FLOP_PER_FRAME = 14.16e6
 FP32_FMA_PEAK_TFLOPS = 73.5            # measured on this pool with tools/microbench_fma.cu (FFMA2), see DESIGN.md
+# dram__bytes_read+write summed over the 78 conv launches of one HiFiGAN pass at this workload's shape (B=32, 192
+# padded frames), from one ncu capture: profiles/r01_decoder_dram_traffic.csv (19.8 GB read + 8.9 GB written)
+DECODER_DRAM_BYTES_PER_PASS = {6144: 28.72e9}
 
 
 def load_peaks():
@@ -288,7 +291,9 @@ def run_cuda(args):
             "roofline": {"bound": "tensor", "kernel": "conv1d_tc_kernel + conv1d_kernel (all HiFiGAN launches of a step)",
                          "achieved": dec_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (dec_tflops / peaks["bf16_tflops_sustained"]) if dec_tflops else None,
-                         "traffic": None, "peak_source": peaks["source"],
+                         "traffic": DECODER_DRAM_BYTES_PER_PASS.get(frames_padded // args.steps),
+                         "traffic_unit": "bytes per decoder pass (78 launches), ncu dram__bytes_read+write; algorithmic layer-granular = 21.2 KB/sample",
+                         "peak_source": peaks["source"],
                          "note": "algorithmic fp32 FLOPs; the MRF/pre convs run on tcgen05 kind::tf32 as 3xTF32 (3 MMAs per "
                                  "algorithmic MAC at half the bf16 rate => ceiling = peak/6), upsamplers/post on the FP32 "
                                  f"FMA pipe (measured peak {FP32_FMA_PEAK_TFLOPS} TFLOP/s)",
