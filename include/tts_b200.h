@@ -106,10 +106,61 @@ typedef struct {
 typedef struct b200tts_flow b200tts_flow;
 int b200tts_flow_create(const b200tts_flow_config* cfg, const float* const* weights, int num_weights,
                         b200tts_flow** out);
+/* same weights, packed for the forward direction (networks.py:223-227; voice conversion, vits.py:1226):
+ * run it with b200tts_flow_reverse() -- the handle remembers its direction */
+int b200tts_flow_create_forward(const b200tts_flow_config* cfg, const float* const* weights, int num_weights,
+                                b200tts_flow** out);
 void b200tts_flow_destroy(b200tts_flow* h);
 size_t b200tts_flow_workspace_bytes(const b200tts_flow* h, int B, int T);
 int b200tts_flow_reverse(const b200tts_flow* h, float* z, const float* mask, const float* g, int B, int T,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- posterior encoder (training / voice conversion) ----------------------------------------
+ * Replaces PosteriorEncoder.forward, TTS/tts/layers/vits/networks.py:275-288.
+ * weights: pre.w [H,Cin,1], pre.b, [enc.cond_layer.w, .b], per WN layer enc.in_layers[i].w,.b, enc.res_skip_layers[i].w,.b,
+ *          proj.w [2*out,H,1], proj.b.
+ * x [B,Cin,T] (linear spectrogram); mask [B,T]; g [B,cond] or NULL; noise [B,out,T] = the randn_like(mean) draw of :287.
+ * outputs: z [B,out,T] = (mean + noise*exp(log_scale))*mask; stats [B,2*out,T] = [mean | log_scale] (masked).
+ */
+typedef struct {
+    int in_channels;
+    int out_channels;
+    int hidden_channels;
+    int kernel_size;
+    int dilation_rate;
+    int num_layers;
+    int cond_channels;
+} b200tts_posterior_config;
+typedef struct b200tts_posterior b200tts_posterior;
+int b200tts_posterior_create(const b200tts_posterior_config* cfg, const float* const* weights, int num_weights,
+                             b200tts_posterior** out);
+void b200tts_posterior_destroy(b200tts_posterior* h);
+size_t b200tts_posterior_workspace_bytes(const b200tts_posterior* h, int B, int T);
+int b200tts_posterior_forward(const b200tts_posterior* h, const float* x, const float* mask, const float* g,
+                              const float* noise, int B, int T, float* z, float* stats, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* ---- deterministic duration predictor (VitsArgs.use_sdp = False) ----------------------------
+ * Replaces DurationPredictor.forward, TTS/tts/layers/glow_tts/duration_predictor.py:44-69.
+ * weights: conv_1.w [F,Cin,k], .b, norm_1.gamma [F], .beta, conv_2.w [F,F,k], .b, norm_2.gamma, .beta, proj.w [1,F,1], .b,
+ *          [cond.w [Cin,cond,1], .b], [cond_lang.w [Cin,L,1], .b]          (Cin = in_channels + language_emb_dim)
+ * x [B,Cin,T]; mask [B,T]; g [B,cond] / lang_emb [B,L] or NULL -> log-durations [B,T].
+ */
+typedef struct {
+    int in_channels;
+    int hidden_channels;
+    int kernel_size;
+    int cond_channels;
+    int language_emb_dim;
+} b200tts_duration_predictor_config;
+typedef struct b200tts_duration_predictor b200tts_duration_predictor;
+int b200tts_duration_predictor_create(const b200tts_duration_predictor_config* cfg, const float* const* weights,
+                                      int num_weights, b200tts_duration_predictor** out);
+void b200tts_duration_predictor_destroy(b200tts_duration_predictor* h);
+size_t b200tts_duration_predictor_workspace_bytes(const b200tts_duration_predictor* h, int B, int T);
+int b200tts_duration_predictor_forward(const b200tts_duration_predictor* h, const float* x, const float* mask,
+                                       const float* g, const float* lang_emb, int B, int T, float* logw,
+                                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- text encoder ----------------------------------------------------------------------------
  * Replaces TextEncoder.forward, TTS/tts/layers/vits/networks.py:80-100 (RelativePositionTransformer

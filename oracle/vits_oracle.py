@@ -429,6 +429,28 @@ def vits_inference(sd, tokens, x_lengths, sdp_noise, prior_noise_fn, *, args, sp
             "logs_p": logs_p, "y_mask": y_mask, "logw": logw, "x": x, "y_lengths": y_lengths}
 
 
+def voice_conversion(sd, y, y_lengths, g_src, g_tgt, posterior_noise, *, args):
+    """Vits.voice_conversion glue, tts/models/vits.py:1226-1232 (g_* already embedded / normalised [B,C,1])."""
+    a = args
+    hid = a["hidden_channels"]
+    z, _, _, y_mask = posterior_encoder(sub(sd, "posterior_encoder"), y, y_lengths, g=g_src, noise=posterior_noise,
+                                        out_channels=hid, hidden=hid,
+                                        kernel_size=a["kernel_size_posterior_encoder"],
+                                        dilation_rate=a["dilation_rate_posterior_encoder"],
+                                        num_layers=a["num_layers_posterior_encoder"])
+    fkw = dict(hidden=hid, kernel_size=a["kernel_size_flow"], dilation_rate=a["dilation_rate_flow"],
+               num_layers=a["num_layers_flow"])
+    z_p = flow_forward(sub(sd, "flow"), z, y_mask, g=g_src, reverse=False, **fkw)
+    z_hat = flow_forward(sub(sd, "flow"), z_p, y_mask, g=g_tgt, reverse=True, **fkw)
+    o_hat = hifigan_forward(sub(sd, "waveform_decoder"), z_hat * y_mask, g=g_tgt,
+                            upsample_factors=a["upsample_rates_decoder"],
+                            upsample_kernel_sizes=a["upsample_kernel_sizes_decoder"],
+                            resblock_kernel_sizes=a["resblock_kernel_sizes_decoder"],
+                            resblock_dilation_sizes=a["resblock_dilation_sizes_decoder"],
+                            resblock_type=a["resblock_type_decoder"])
+    return o_hat, y_mask, (z, z_p, z_hat)
+
+
 # --------------------------------------------------------------------------- MAS
 def maximum_path_numpy_loop(value, t_xs, t_ys, max_neg_val=-1e9):
     """Pure-Python/numpy transcription of core.pyx:11-37 for SMALL cases only."""

@@ -31,7 +31,11 @@ def seq_mask(lengths, t):
 
 
 def save(name, obj):
-    torch.save(obj, os.path.join(HERE, name + ".pt"))
+    path = os.path.join(HERE, name + ".pt")
+    if os.path.exists(path) and "--force" not in sys.argv:   # fixtures are append-only: keep committed bytes stable
+        print("kept ", name)
+        return
+    torch.save(obj, path)
     print("wrote", name)
 
 
@@ -100,6 +104,27 @@ def main():
     dur = torch.randint(1, 4, (10, 21)).float()
     dur_mask = torch.ones(10, 21, int(dur.sum(1).max()))
     save("generate_path", {"duration": dur, "mask": dur_mask, "path": R["helpers"].generate_path(dur, dur_mask)})
+    # 8. posterior encoder (voice conversion); the reference draws randn_like(mean) inside forward (networks.py:287)
+    args = dict(in_channels=33, out_channels=16, hidden_channels=24, kernel_size=5, dilation_rate=1, num_layers=3,
+                cond_channels=10)
+    m = R["networks"].PosteriorEncoder(**args).eval()
+    y, g3 = torch.randn(3, 33, 29).abs(), torch.randn(3, 10, 1)
+    ylen = torch.tensor([29, 14, 3])
+    torch.manual_seed(99)
+    noise = torch.randn(3, 16, 29)
+    torch.manual_seed(99)
+    z, mean, log_scale, ymask = m(y, ylen, g=g3)
+    save("posterior_small", {"args": args, "state": m.state_dict(), "y": y, "y_lengths": ylen, "g": g3,
+                             "noise": noise, "z": z, "mean": mean, "log_scale": log_scale, "y_mask": ymask})
+    # 9. deterministic duration predictor (use_sdp=False), speaker + language conditioned
+    args = dict(in_channels=16, hidden_channels=32, kernel_size=3, dropout_p=0.5, cond_channels=10, language_emb_dim=4)
+    m = R["duration_predictor"].DurationPredictor(**args).eval()
+    for p_ in m.parameters():           # default init leaves gamma=0.1/beta=0: make every parameter informative
+        p_.data.add_(torch.randn_like(p_) * 0.05)
+    xd, gd, ld = torch.randn(4, 20, 23), torch.randn(4, 10, 1), torch.randn(4, 4, 1)
+    xmd = seq_mask(torch.tensor([23, 17, 9, 2]), 23)
+    save("duration_predictor_small", {"args": args, "state": m.state_dict(), "x": xd, "x_mask": xmd, "g": gd,
+                                      "lang_emb": ld, "logw": m(xd, xmd, g=gd, lang_emb=ld)})
 
 
 if __name__ == "__main__":

@@ -54,6 +54,24 @@ def test_sdp_reverse(golden):
     assert torch.allclose(logw, g["logw"], atol=1e-6, rtol=0)
 
 
+def test_posterior_encoder(golden):
+    g = golden("posterior_small")
+    a = g["args"]
+    z, mean, logs, mask = O.posterior_encoder(g["state"], g["y"], g["y_lengths"], g=g["g"], noise=g["noise"],
+                                              out_channels=a["out_channels"], hidden=a["hidden_channels"],
+                                              kernel_size=a["kernel_size"], dilation_rate=a["dilation_rate"],
+                                              num_layers=a["num_layers"])
+    for got, key in ((z, "z"), (mean, "mean"), (logs, "log_scale"), (mask, "y_mask")):
+        assert torch.equal(got, g[key]), key
+
+
+def test_deterministic_duration_predictor(golden):
+    g = golden("duration_predictor_small")
+    logw = O.duration_predictor(g["state"], g["x"], g["x_mask"], g=g["g"], lang_emb=g["lang_emb"])
+    assert torch.allclose(logw, g["logw"], atol=1e-6, rtol=0)
+    assert logw.shape == (4, 1, 23)
+
+
 def test_mas_ports_match_reference_kernel(golden):
     for case in golden("mas_cases")["cases"]:
         for impl in ("c", "py"):

@@ -69,8 +69,80 @@ def test_flow_golden(golden):
     m.cuda()
     got = m(g["z"].cuda(), g["mask"].cuda(), g=g["g"].cuda(), reverse=True)
     _close(got, g["rev"], 2e-5, "flow reverse")
-    with pytest.raises(NotImplementedError):
-        m(g["z"].cuda(), g["mask"].cuda(), g=g["g"].cuda(), reverse=False)
+    got = m(g["z"].cuda(), g["mask"].cuda(), g=g["g"].cuda(), reverse=False)
+    _close(got, g["fwd"], 2e-5, "flow forward")
+
+
+@pytest.mark.parametrize("flows", [3, 4])
+def test_flow_forward_then_reverse_is_identity(flows):
+    """Size-independent property (networks.py:214-232): reverse(forward(z)) == z on the unmasked frames, also for an
+    odd number of flows (one channel flip left over after folding the rest into the packed weights)."""
+    from tts_b200.layers import ResidualCouplingBlocks
+    torch.manual_seed(flows)
+    m = ResidualCouplingBlocks(192, 192, 5, 1, 4, num_flows=flows, cond_channels=64).eval()
+    _perturb(m)
+    z, g = torch.randn(2, 192, 301), torch.randn(2, 64, 1)
+    mask = (torch.arange(301)[None, :] < torch.tensor([301, 77])[:, None]).float().unsqueeze(1)
+    kw = dict(num_flows=flows, hidden=192, kernel_size=5, dilation_rate=1, num_layers=4)
+    want = O.flow_forward(m.state_dict(), z, mask, g, reverse=False, **kw)
+    m.cuda()
+    zp = m(z.cuda(), mask.cuda(), g=g.cuda(), reverse=False)
+    _close(zp, want, 1e-4, "flow forward vs oracle")
+    back = m(zp, mask.cuda(), g=g.cuda(), reverse=True)
+    _close(back * mask.cuda(), z * mask, 2e-4, "round trip")
+
+
+def test_posterior_encoder_golden(golden):
+    from tts_b200.layers import PosteriorEncoder
+    g = golden("posterior_small")
+    m = PosteriorEncoder(**g["args"]).eval()
+    m.load_state_dict(g["state"])
+    m.cuda()
+    z, mean, logs, mask = m(g["y"].cuda(), g["y_lengths"].cuda(), g=g["g"].cuda(), noise=g["noise"].cuda())
+    _close(mean, g["mean"], 3e-5, "mean")
+    _close(logs, g["log_scale"], 3e-5, "log_scale")
+    _close(z, g["z"], 5e-5, "z")
+    assert torch.equal(mask.cpu(), g["y_mask"])
+
+
+def test_posterior_encoder_full_width_vs_oracle():
+    from tts_b200.layers import PosteriorEncoder
+    torch.manual_seed(11)
+    m = PosteriorEncoder(513, 192, 192, 5, 1, 16, cond_channels=256).eval()
+    y, g = torch.randn(2, 513, 203).abs(), torch.randn(2, 256, 1)
+    lens = torch.tensor([203, 90])
+    noise = torch.randn(2, 192, 203)
+    want = O.posterior_encoder(m.state_dict(), y, lens, g=g, noise=noise)
+    m.cuda()
+    got = m(y.cuda(), lens.cuda(), g=g.cuda(), noise=noise.cuda())
+    for a, w, n in zip(got, want, ("z", "mean", "log_scale", "mask")):
+        _close(a, w, 2e-4, n)
+
+
+def test_duration_predictor_golden(golden):
+    from tts_b200.layers import DurationPredictor
+    g = golden("duration_predictor_small")
+    m = DurationPredictor(**g["args"]).eval()
+    m.load_state_dict(g["state"])
+    m.cuda()
+    got = m(g["x"].cuda(), g["x_mask"].cuda(), g=g["g"].cuda(), lang_emb=g["lang_emb"].cuda())
+    _close(got, g["logw"], 2e-5, "logw")
+
+
+@pytest.mark.parametrize("cond", [0, 256])
+def test_duration_predictor_full_width_vs_oracle(cond):
+    from tts_b200.layers import DurationPredictor
+    torch.manual_seed(cond + 3)
+    m = DurationPredictor(192, 256, 3, 0.5, cond_channels=cond).eval()
+    for p in m.parameters():
+        p.data.add_(torch.randn_like(p) * 0.05)
+    x = torch.randn(3, 192, 57)
+    mask = (torch.arange(57)[None, :] < torch.tensor([57, 30, 1])[:, None]).float().unsqueeze(1)
+    g = torch.randn(3, cond, 1) if cond else None
+    want = O.duration_predictor(m.state_dict(), x, mask, g=g)
+    m.cuda()
+    got = m(x.cuda(), mask.cuda(), g=None if g is None else g.cuda())
+    _close(got, want, 5e-5, "logw")
 
 
 @pytest.mark.parametrize("cond", [0, 256])

@@ -56,9 +56,31 @@ static std::vector<float> pack_tc(const std::vector<float>& W, int Cout, int Cin
     return P;
 }
 
+static std::vector<float> pack_grouped(const std::vector<float>& W, int Cout, int Cin, int K, int G) {
+    const int J = (K + G - 1) / G, nchunk = (Cin + KC - 1) / KC, cpw = 32 / G;
+    const size_t blk = (size_t)2 * NSLAB * 128 * 4;
+    std::vector<float> P((size_t)nchunk * J * blk, 0.f);
+    for (int c = 0; c < nchunk; ++c)
+        for (int j = 0; j < J; ++j) {
+            float* dst = P.data() + ((size_t)c * J + j) * blk;
+            for (int s = 0; s < NSLAB; ++s)
+                for (int m = 0; m < 128; ++m)
+                    for (int i = 0; i < 4; ++i) {
+                        const int q = m / 32, l = m % 32, co = q * cpw + l / G, g = l % G, k = G * j + g, ci = c * KC + 4 * s + i;
+                        float v = (ci < Cin && k < K) ? W[((size_t)co * Cin + ci) * K + k] : 0.f;
+                        uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u;
+                        float hi; memcpy(&hi, &u, 4);
+                        dst[((size_t)s * 128 + m) * 4 + i] = hi;
+                        dst[((size_t)(NSLAB + s) * 128 + m) * 4 + i] = v - hi;
+                    }
+        }
+    return P;
+}
+
 static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum, int iters) {
     const int Cout = C, pad = (K * dil - dil) / 2;
     const bool v3 = getenv("TC_V3") != nullptr;
+    const int G = (v3 && getenv("TC_G") && (C == 32 || C == 64)) ? 128 / C : 1;
     const int N = v3 ? 128 : (Cout > 128 ? 128 : Cout);
     printf("case B=%d C=%d T=%d K=%d dil=%d res=%d accum=%d N=%d: ", B, C, T, K, dil, with_res, accum, N);
     fflush(stdout);
@@ -69,7 +91,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     for (auto& v : hb) v = (rand() / (float)RAND_MAX - 0.5f);
     for (auto& v : hr) v = (rand() / (float)RAND_MAX - 0.5f);
     for (auto& v : hy0) v = (rand() / (float)RAND_MAX - 0.5f);
-    std::vector<float> hp = pack_tc(hw, Cout, C, K, N);
+    std::vector<float> hp = G > 1 ? pack_grouped(hw, Cout, C, K, G) : pack_tc(hw, Cout, C, K, N);
     float *dx, *dw, *dp, *db, *dr, *dy, *dyr; int* derr;
     CK(cudaMalloc(&dx, hx.size() * 4)); CK(cudaMalloc(&dw, hw.size() * 4)); CK(cudaMalloc(&dp, hp.size() * 4));
     CK(cudaMalloc(&db, hb.size() * 4)); CK(cudaMalloc(&dr, hr.size() * 4)); CK(cudaMalloc(&dy, hy0.size() * 4));
@@ -106,13 +128,24 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
         a3.y = dy; a3.y_bs = a.y_bs; a3.y_cs = T; a3.Tout = T; a3.ups = 1; a3.Tq = T;
         a3.res = a.res; a3.res_bs = a.res_bs; a3.res_cs = a.res_cs; a3.scale = scale; a3.post_div = 1.f; a3.accum = accum;
         a3.rows_pad = a.rows_pad; a3.raw_w = a.rows_pad + 4; a3.B = B; a3.n_ttiles = (T + 255) / 256; a3.n_rtiles = (Cout + 127) / 128;
-        a3.err = derr;
+        a3.err = derr; a3.dbg = a.dbg;
+        a3.KJ = K; a3.dil_blk = dil; a3.tstep = 256;
+        if (G > 1) {
+            const int J = (K + G - 1) / G;
+            a3.KJ = J; a3.dil_blk = G * dil; a3.tstep = TSTEP_GROUPED;
+            a3.rows_pad = (256 + (J - 1) * G * dil + 7) / 8 * 8; a3.raw_w = a3.rows_pad + 4;
+            a3.n_ttiles = (T + a3.tstep - 1) / a3.tstep; a3.n_rtiles = 1;
+        }
         smem2 = smem_bytes3(a3.rows_pad, a3.raw_w);
+        CK(cudaFuncSetAttribute(conv1d_tc3g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(conv1d_tc3g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         const int tiles = a3.B * a3.n_ttiles * a3.n_rtiles;
         grid2 = dim3(tiles < sms ? tiles : sms);
-        conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        if (G == 2) conv1d_tc3g2_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        else if (G == 4) conv1d_tc3g4_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        else conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
     } else if (v2) {
         using namespace b200tts::tc2;
         a2.x = dx; a2.x_bs = a.x_bs; a2.x_cs = T; a2.Tin = T; a2.in_slope = slope; a2.w = dp; a2.bias = db;
@@ -143,12 +176,15 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
         if (fabs(hyr[i]) > maxref) maxref = fabs(hyr[i]);
         sumsq += d * d;
     }
+    if (G > 1) printf("grouped G=%d ", G);
     printf("%s smem=%zu err_flag=%d max_err=%.3e rms_err=%.3e max_ref=%.3f  %s", v3 ? "v3" : (v2 ? "v2" : "v1"), (v2 || v3) ? smem2 : smem, herr, maxerr, sqrt(sumsq / hy.size()), maxref,
            (herr == 0 && maxerr < 1e-4 * (maxref + 1)) ? "OK" : "MISMATCH");
     if (getenv("TC_TRACE") && v3) {
         unsigned long long* dtr; CK(cudaMalloc(&dtr, (size_t)grid2.x * 32 * 8)); CK(cudaMemset(dtr, 0, (size_t)grid2.x * 32 * 8));
         a3.trace = dtr;
-        b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        if (G == 2) b200tts::tc3::conv1d_tc3g2_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        else if (G == 4) b200tts::tc3::conv1d_tc3g4_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        else b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         CK(cudaDeviceSynchronize());
         std::vector<unsigned long long> tr((size_t)grid2.x * 32);
         CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
@@ -195,7 +231,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (iters > 0 && herr == 0 && !accum) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        for (int i = 0; i < iters; ++i) { if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
+        for (int i = 0; i < iters; ++i) { if (v3 && G == 2) b200tts::tc3::conv1d_tc3g2_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3 && G == 4) b200tts::tc3::conv1d_tc3g4_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
         printf("  %.3f ms  %.1f TFLOP/s (algorithmic fp32)", ms, 2.0 * B * Cout * (double)C * K * T / ms / 1e9);
@@ -214,12 +250,19 @@ int main(int argc, char** argv) {
     fails += run_case(2, 128, 700, 11, 5, 1, 0, 0);
     fails += run_case(2, 256, 300, 3, 3, 1, 1, 0);
     fails += run_case(2, 64, 1000, 7, 3, 0, 0, 0);
+    fails += run_case(2, 64, 1004, 11, 5, 1, 1, 0);
+    fails += run_case(3, 32, 996, 11, 5, 1, 0, 0);
+    fails += run_case(2, 32, 2000, 7, 1, 1, 1, 0);
+    fails += run_case(2, 32, 480, 3, 3, 0, 0, 0);
     if (fails == 0 || (argc > 1 && !strcmp(argv[1], "time"))) {
         run_case(32, 128, 9600, 11, 5, 1, 0, 5);       // HiFiGAN stage 1 at cfg2
         run_case(32, 128, 9600, 3, 1, 1, 0, 5);
         run_case(32, 256, 1200, 7, 3, 1, 0, 5);
         run_case(32, 64, 19200, 11, 1, 1, 0, 5);
+        run_case(32, 64, 19200, 3, 1, 1, 0, 5);
         run_case(32, 32, 38400, 7, 1, 1, 0, 5);
+        run_case(32, 32, 38400, 3, 1, 1, 0, 5);
+        run_case(32, 32, 38400, 11, 5, 1, 0, 5);
     }
     printf("FAILS=%d\n", fails);
     return fails;

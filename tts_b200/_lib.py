@@ -47,6 +47,16 @@ class SdpConfigC(ctypes.Structure):
                [("tail_bound", ctypes.c_float)]
 
 
+class PosteriorConfigC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("in_channels", "out_channels", "hidden_channels", "kernel_size",
+                                            "dilation_rate", "num_layers", "cond_channels")]
+
+
+class DurationPredictorConfigC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("in_channels", "hidden_channels", "kernel_size", "cond_channels",
+                                            "language_emb_dim")]
+
+
 def _declare(lib):
     vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     lib.b200tts_last_error.restype = ctypes.c_char_p
@@ -68,7 +78,8 @@ def _declare(lib):
     lib.b200tts_hifigan_forward.restype = ci
     lib.b200tts_hifigan_forward.argtypes = [vp, vp, vp, ci, ci, vp, vp, sz, vp]
     cf = ctypes.c_float
-    for name, cfgt in (("flow", FlowConfigC), ("text_encoder", TextEncoderConfigC), ("sdp", SdpConfigC)):
+    for name, cfgt in (("flow", FlowConfigC), ("text_encoder", TextEncoderConfigC), ("sdp", SdpConfigC),
+                       ("posterior", PosteriorConfigC), ("duration_predictor", DurationPredictorConfigC)):
         f = getattr(lib, f"b200tts_{name}_create")
         f.restype = ci
         f.argtypes = [ctypes.POINTER(cfgt), ctypes.POINTER(vp), ci, ctypes.POINTER(vp)]
@@ -86,6 +97,12 @@ def _declare(lib):
     lib.b200tts_stft_magnitude.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, vp, ci, vp]
     lib.b200tts_stft_mel_project.restype = ci
     lib.b200tts_stft_mel_project.argtypes = [vp, vp, ci, ci, cf, vp, vp]
+    lib.b200tts_flow_create_forward.restype = ci
+    lib.b200tts_flow_create_forward.argtypes = [ctypes.POINTER(FlowConfigC), ctypes.POINTER(vp), ci, ctypes.POINTER(vp)]
+    lib.b200tts_posterior_forward.restype = ci
+    lib.b200tts_posterior_forward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, sz, vp]
+    lib.b200tts_duration_predictor_forward.restype = ci
+    lib.b200tts_duration_predictor_forward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, sz, vp]
     lib.b200tts_flow_reverse.restype = ci
     lib.b200tts_flow_reverse.argtypes = [vp, vp, vp, vp, ci, ci, vp, sz, vp]
     lib.b200tts_text_encoder_forward.restype = ci

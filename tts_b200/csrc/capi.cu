@@ -10,6 +10,8 @@ struct b200tts_flow { Flow impl; };
 struct b200tts_text_encoder { TextEncoder impl; };
 struct b200tts_sdp { SDP impl; };
 struct b200tts_stft { Stft impl; };
+struct b200tts_posterior { PosteriorEnc impl; };
+struct b200tts_duration_predictor { DurPred impl; };
 
 extern "C" {
 
@@ -55,6 +57,17 @@ int b200tts_flow_create(const b200tts_flow_config* cfg, const float* const* weig
     b200tts_flow* h = new (std::nothrow) b200tts_flow();
     if (!h) { set_error("flow_create: out of host memory"); return 1; }
     int rc = h->impl.init(*cfg, weights, num_weights);
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+int b200tts_flow_create_forward(const b200tts_flow_config* cfg, const float* const* weights, int num_weights,
+                                b200tts_flow** out) {
+    if (!cfg || !weights || !out) { set_error("flow_create_forward: null argument"); return 1; }
+    *out = nullptr;
+    b200tts_flow* h = new (std::nothrow) b200tts_flow();
+    if (!h) { set_error("flow_create_forward: out of host memory"); return 1; }
+    int rc = h->impl.init(*cfg, weights, num_weights, 1);
     if (rc) { delete h; return rc; }
     *out = h;
     return 0;
@@ -145,6 +158,36 @@ int b200tts_stft_mel_project(const b200tts_stft* h, const float* spec, int B, in
                              float* mel, void* stream) {
     if (!h) { set_error("stft_mel_project: null handle"); return 1; }
     return h->impl.mel_project(spec, B, n_frames, log_clamp, mel, (cudaStream_t)stream);
+}
+
+#define B200_HANDLE_API(NAME, TYPE, CFG)                                                                        \
+    int b200tts_##NAME##_create(const CFG* cfg, const float* const* weights, int num_weights, TYPE** out) {       \
+        if (!cfg || !weights || !out) { set_error(#NAME "_create: null argument"); return 1; }                   \
+        *out = nullptr;                                                                                          \
+        TYPE* h = new (std::nothrow) TYPE();                                                                     \
+        if (!h) { set_error(#NAME "_create: out of host memory"); return 1; }                                    \
+        int rc = h->impl.init(*cfg, weights, num_weights);                                                       \
+        if (rc) { delete h; return rc; }                                                                         \
+        *out = h;                                                                                                \
+        return 0;                                                                                                \
+    }                                                                                                            \
+    void b200tts_##NAME##_destroy(TYPE* h) { delete h; }                                                         \
+    size_t b200tts_##NAME##_workspace_bytes(const TYPE* h, int B, int T) { return h ? h->impl.workspace_bytes(B, T) : 0; }
+
+B200_HANDLE_API(posterior, b200tts_posterior, b200tts_posterior_config)
+B200_HANDLE_API(duration_predictor, b200tts_duration_predictor, b200tts_duration_predictor_config)
+
+int b200tts_posterior_forward(const b200tts_posterior* h, const float* x, const float* mask, const float* g,
+                              const float* noise, int B, int T, float* z, float* stats, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!h) { set_error("posterior_forward: null handle"); return 1; }
+    return h->impl.forward(x, mask, g, noise, B, T, z, stats, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int b200tts_duration_predictor_forward(const b200tts_duration_predictor* h, const float* x, const float* mask,
+                                       const float* g, const float* lang_emb, int B, int T, float* logw,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) { set_error("duration_predictor_forward: null handle"); return 1; }
+    return h->impl.forward(x, mask, g, lang_emb, B, T, logw, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

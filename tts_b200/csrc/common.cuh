@@ -66,6 +66,8 @@ struct ConvLayer {            // immutable after pack(); owned by an engine hand
     int tr_kernel = 0, tr_pad = 0;  // original transposed-conv kernel size / padding (for Tout)
     float* w_tc = nullptr;    // device, tcgen05 packing [n_tile][chunk][tap]{hi,lo}[slab][N][4] (null: layer not eligible)
     int tc_n = 0;             // columns (output rows) per tcgen05 CTA
+    float* w_tcg = nullptr;   // device, grouped tcgen05 packing [chunk][tap block]{hi,lo}[slab][128][4] (rows == 32 / 64)
+    int tc_grp = 0;           // tap groups of the grouped packing (128 / rows), 0: none
     bool allow_tc = false;    // engines opt layers into the 3xTF32 tensor-core path (decoder / flow); the text and
                               // duration path stays on the exact FP32 FMA kernel so durations remain bit-stable
 };

@@ -373,7 +373,8 @@ void free_conv(ConvLayer& L) {
     if (L.w) cudaFree(L.w);
     if (L.bias) cudaFree(L.bias);
     if (L.w_tc) cudaFree(L.w_tc);
-    L.w = L.bias = L.w_tc = nullptr;
+    if (L.w_tcg) cudaFree(L.w_tcg);
+    L.w = L.bias = L.w_tc = L.w_tcg = nullptr;
 }
 
 // Wl(r, ci, k): logical weights already expressed as a correlation-form conv with `rows` GEMM rows
@@ -429,6 +430,35 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
         if (upload(&L.w_tc, Q.data(), Q.size())) return 2;
     } else {
         L.tc_n = 0;
+    }
+    // grouped packing for exactly 32 / 64 rows (conv_tc3.cuh, grouped mode): MMA row m = quarter*32 + cc*G + g holds
+    // channel co = quarter*(32/G) + cc and tap group g; tap block j carries tap G*j + g (zero beyond K)
+    L.tc_grp = 0;
+    if (L.ups == 1 && (rows == 32 || rows == 64) && Cin >= 8) {
+        using namespace tc;
+        const int G = 128 / rows, J = (K + G - 1) / G, nchunk = (Cin + KC - 1) / KC, cpw = 32 / G;
+        const size_t blk = (size_t)2 * NSLAB * 128 * 4;
+        std::vector<float> Q((size_t)nchunk * J * blk, 0.f);
+        for (int c = 0; c < nchunk; ++c)
+            for (int j = 0; j < J; ++j) {
+                float* dst = Q.data() + ((size_t)c * J + j) * blk;
+                for (int s2 = 0; s2 < NSLAB; ++s2)
+                    for (int m = 0; m < 128; ++m)
+                        for (int i = 0; i < 4; ++i) {
+                            const int q = m / 32, l = m % 32, co = q * cpw + l / G, g = l % G;
+                            const int k = G * j + g, ci = c * KC + 4 * s2 + i;
+                            const float v = (ci < Cin && k < K) ? Wl[((size_t)co * Cin + ci) * K + k] : 0.f;
+                            uint32_t u;
+                            memcpy(&u, &v, 4);
+                            u &= 0xFFFFE000u;
+                            float hi;
+                            memcpy(&hi, &u, 4);
+                            dst[((size_t)s2 * 128 + m) * 4 + i] = hi;
+                            dst[((size_t)(NSLAB + s2) * 128 + m) * 4 + i] = v - hi;
+                        }
+            }
+        if (upload(&L.w_tcg, Q.data(), Q.size())) return 2;
+        L.tc_grp = G;
     }
     return 0;
 }
@@ -527,8 +557,10 @@ static int launch_cic(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaS
 // tcgen05 path: returns -1 when the layer / shape / epilogue is not eligible (caller falls through to the FMA kernel)
 static int* g_tc_err = nullptr;
 static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
-    static int enabled = -1, v2_enabled = -1, num_sms = 0;
+    static int enabled = -1, v2_enabled = -1, grouped_enabled = 1, num_sms = 0;
     if (enabled < 0) {
+        const char* e3 = getenv("B200TTS_NO_TCG");
+        grouped_enabled = (e3 && atoi(e3)) ? 0 : 1;
         const char* e = getenv("B200TTS_NO_TC");
         enabled = (e && atoi(e)) ? 0 : 1;
         const char* e2 = getenv("B200TTS_NO_TC2");
@@ -542,6 +574,8 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc2::conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaMalloc((void**)&g_tc_err, sizeof(int)));
         B200_CUDA_OK(cudaMemset(g_tc_err, 0, sizeof(int)));
         int dev = 0;
@@ -555,6 +589,33 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
     const int n_rtiles = (L.Rows + L.tc_n - 1) / L.tc_n;
     const bool persistent_ok = v2_enabled && aligned && !a.xmask &&
                                (L.ups == 1 || (!a.res && !(a.flags & EPI_ACCUM) && !a.ymask && !a.cond));
+    if (grouped_enabled && persistent_ok && L.tc_grp && L.w_tcg && L.ups == 1 && !needs_v3 && !a.ymask &&
+        (L.tc_grp - 1) * L.dil <= 15 && a.Tq >= 256) {
+        // grouped mode of the third-generation kernel: M = tap groups x channels, N = 256 time steps, 240 per tile
+        const int G = L.tc_grp, J = (L.K + G - 1) / G;
+        const int rp = (tc3::TT2 + (J - 1) * G * L.dil + 7) / 8 * 8;
+        if (rp <= 320 && tc3::smem_bytes3(rp, rp + 4) <= 227 * 1024) {
+            tc3::Tc3Args t;
+            memset(&t, 0, sizeof(t));
+            t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin; t.in_slope = a.in_slope;
+            t.w = L.w_tcg; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
+            t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = 128;
+            t.KJ = J; t.dil_blk = G * L.dil; t.tstep = tc3::TSTEP_GROUPED;
+            t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout; t.ups = 1; t.Tq = a.Tq;
+            t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
+            t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
+            t.rows_pad = rp; t.raw_w = rp + 4;
+            t.B = io.B; t.n_ttiles = (a.Tq + t.tstep - 1) / t.tstep; t.n_rtiles = 1;
+            t.err = g_tc_err;
+            const long long tiles = (long long)t.B * t.n_ttiles;
+            const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+            if (G == 2) tc3::conv1d_tc3g2_kernel<<<grid, tc3::NTHREADS2, tc3::smem_bytes3(rp, rp + 4), st>>>(t);
+            else tc3::conv1d_tc3g4_kernel<<<grid, tc3::NTHREADS2, tc3::smem_bytes3(rp, rp + 4), st>>>(t);
+            count_launch();
+            B200_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     if (persistent_ok && L.tc_n == 128 && tc3::smem_bytes3(rows_pad, rows_pad + 4) <= 227 * 1024) {
         // third generation: M = rows (128, zero padded), N = 256 time steps
         tc3::Tc3Args t;
@@ -562,6 +623,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin; t.in_slope = a.in_slope;
         t.w = L.w_tc; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
         t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = 128;
+        t.KJ = L.K; t.dil_blk = L.dil; t.tstep = tc3::TT2;
         t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout; t.ups = L.ups; t.Tq = a.Tq;
         t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
         t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;

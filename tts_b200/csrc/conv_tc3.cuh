@@ -12,6 +12,14 @@
 //   warp  9          MMA       : one lane issues 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per tap and chunk, commits to mbarriers
 //   warps 0-3,10-13  epilogue  : lane = output row, columns = time: TMEM -> registers -> float4 global stores (two halves
 //                                of the 256 columns), residual / accumulate loads as float4 with an order-enforced prefetch
+//
+// Grouped mode (GRP = 2 / 4) for narrow layers (exactly 64 / 32 output rows, the last two HiFiGAN stages): the 128
+// MMA rows are GRP tap-groups x (128/GRP) channels -- row (channel c, group g) carries the weights of taps g, g+GRP,
+// g+2*GRP, ... so one instruction stream of ceil(K/GRP) "tap blocks" (B shifted by GRP*dil rows per block) replaces K
+// of them and no MMA row is zero padding.  D_g[c, col] then still misses its own g*dil shift; the epilogue applies it
+// as a TMEM column offset (one tcgen05.ld per group), and sums the GRP partials, which live in adjacent lanes of one
+// warp, with a shuffle reduce-scatter.  Tiles advance by 240 columns so every shifted read stays inside the
+// 256-column accumulator.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -49,11 +57,15 @@ struct Tc3Args {
     int gate;                  // rows are (tanh, sigmoid) pairs: out[r/2] = tanh(v[2p]) * sigmoid(v[2p+1])  (WaveNet)
     int split;                 // > 0: rows < split -> y (accumulate, mask); rows >= split -> y2 (accumulate iff accum2)
     float* y2; long long y2_bs; int y2_cs; int accum2;
+    int KJ;                    // tap blocks per chunk (= K, or ceil(K / GRP) in grouped mode)
+    int dil_blk;               // B-row shift between tap blocks (= dil, or GRP * dil)
+    int tstep;                 // time steps a tile advances (= TT2, or 240 in grouped mode)
     int rows_pad;              // slab rows  (TT2 + halo, multiple of 8)
     int raw_w;                 // raw row width in floats (rows_pad + 4, multiple of 4)
     int B, n_ttiles, n_rtiles;
     int* err;
     unsigned long long* trace;  // optional [grid][32] globaltimer stamps (debug)
+    int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA
 };
 
 static inline size_t smem_bytes3(int rows_pad, int raw_w) {
@@ -67,10 +79,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 
 #define TC3_STAMP(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime(); } while (0)
 
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) {
+constexpr int TSTEP_GROUPED = 240;   // 15 chunks of 16 columns: leaves room for the (GRP-1)*dil <= 15 column shift
+
+template <int GRP>
+__device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ROWS = a.rows_pad, RAWW = a.raw_w, K = a.K;
+    const int ROWS = a.rows_pad, RAWW = a.raw_w, K = a.KJ;
     const uint32_t rawStage = (uint32_t)KC2 * RAWW * 4;
     const uint32_t slabA = (uint32_t)ROWS * 16, stageA = 4 * slabA;     // hi[2] + lo[2]
     const uint32_t slabB = (uint32_t)MROWS * 16, stageB = 4 * slabB;   // one tap block: {hi,lo}[2 slabs][128 rows][16 B]
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
         const int tt = tile % a.n_ttiles, rest = tile / a.n_ttiles;
         rt = rest % a.n_rtiles;
         b = rest / a.n_rtiles;
-        q0 = tt * TT2;
+        q0 = tt * a.tstep;
     };
 
     if (warp >= 4 && warp < 8) {
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
             i_dst[e] = (int)(sl * slabA) + r * 16;
         }
         auto issue = [&](int g) {
-            if (g < total) {
+            if (g < total && !(a.dbg & 1)) {
                 const int it = g / nchunks, c = g - it * nchunks;
                 int b, rt, q0;
                 decode(it, b, rt, q0);
@@ -180,6 +195,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
             const float* raw = reinterpret_cast<const float*>(smRaw + (g % NRAW) * rawStage) + off;
             unsigned char* base = smA + as * stageA;
             float u[MAXI][4];
+            if (!(a.dbg & 2)) {
 #pragma unroll
             for (int e = 0; e < MAXI; ++e) {           // all shared loads first ...
                 const int o = i_raw[e] < 0 ? 0 : i_raw[e];
@@ -201,6 +217,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
                 }
                 *reinterpret_cast<float4*>(base + i_dst[e]) = hi;
                 *reinterpret_cast<float4*>(base + 2 * slabA + i_dst[e]) = lo;
+            }
             }
             fence_async_smem();
             mbar_arrive(BAR(A_FULL + as));
@@ -256,10 +273,12 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
                         const uint32_t bbase = smem_u32(smB + sb * stageB);
                         const uint64_t w_hi = make_desc(bbase, slabB);
                         const uint64_t w_lo = w_hi + (uint64_t)((2 * slabB) >> 4);
-                        const uint64_t xrow = (uint64_t)(k * a.dil);
+                        const uint64_t xrow = (uint64_t)(k * a.dil_blk);
+                        if (!(a.dbg & 16)) {
                         mma_tf32(dcol, w_hi, x_lo0 + xrow, idesc, (c == 0 && k == 0) ? 0u : 1u);   // small terms first
                         mma_tf32(dcol, w_lo, x_hi0 + xrow, idesc, 1u);
                         mma_tf32(dcol, w_hi, x_hi0 + xrow, idesc, 1u);
+                        }
                         mma_commit(BAR(B_EMPTY + sb));
                     }
                     if (ok) mma_commit(BAR(A_EMPTY + sa));
@@ -284,6 +303,109 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
             if (!ok) break;
             tc_fence_after();
             if (tid == 0) { if (it == 0) TC3_STAMP(16); if (it == 1) TC3_STAMP(18); if (it == 3) TC3_STAMP(20); }
+            if constexpr (GRP > 1) {
+                // ---- grouped epilogue: lane = (channel cc, tap group g); out[c, t] = sum_g D_g[c, t + g*dil]
+                constexpr int CPW = 32 / GRP, NV = 16 / GRP;
+                const int g = lane & (GRP - 1), cc = lane / GRP;
+                const int co = lq * CPW + cc;                                   // Rows == 128 / GRP
+                const uint32_t dlane = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16);
+                const int coff = (GRP == 4) ? ((g & 1) * 8 + (g >> 1) * 4) : g * 8;   // this lane's columns in a chunk
+                const int cbeg = half ? 128 : 0, cend = half ? a.tstep : min(128, a.tstep);
+                float bias = a.bias[co];
+                if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + co);
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs;
+                const float* rrow = a.res ? a.res + (long long)b * a.res_bs + (long long)co * a.res_cs : nullptr;
+                const bool acc_r = a.accum != 0 && !(a.dbg & 4);
+                if (a.dbg & 4) rrow = nullptr;
+                const bool vec_ok = ((a.y_cs & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
+                                    ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
+                                    (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+                float rv[NV], ov[NV];
+                auto prefetch = [&](int cg, float* r_, float* o_) {
+                    const int q = q0 + cg + coff;
+#pragma unroll
+                    for (int j = 0; j < NV / 4; ++j) {
+                        const int qq = q + 4 * j;
+                        if (vec_ok && qq + 3 < a.Tout) {
+                            if (rrow) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rrow + qq));
+                            if (acc_r) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int qe = min(qq + e, a.Tout - 1);
+                                if (rrow) asm volatile("ld.global.f32 %0, [%1];" : "=f"(r_[4 * j + e]) : "l"(rrow + qe));
+                                if (acc_r) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
+                            }
+                        }
+                    }
+                };
+                prefetch(cbeg, rv, ov);
+                for (int cg = cbeg; cg < cend; cg += 16) {
+                    float rn[NV], on[NV], P[16];
+                    if (cg + 16 < cend) prefetch(cg + 16, rn, on);
+                    {
+                        float l0[16], l1[16];
+                        tmem_ld16(dlane + (uint32_t)cg, l0);
+                        tmem_ld16(dlane + (uint32_t)(cg + a.dil), l1);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) P[i] = (g & 1) ? l1[i] : l0[i];
+                    }
+                    if constexpr (GRP == 4) {
+                        float l2[16], l3[16];
+                        tmem_ld16(dlane + (uint32_t)(cg + 2 * a.dil), l2);
+                        tmem_ld16(dlane + (uint32_t)(cg + 3 * a.dil), l3);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { const float hi2 = (g & 1) ? l3[i] : l2[i]; P[i] = (g & 2) ? hi2 : P[i]; }
+                    }
+                    // shuffle reduce-scatter over the GRP adjacent lanes of a channel
+                    float S[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float send = (g & 1) ? P[i] : P[i + 8];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                        S[i] = ((g & 1) ? P[i + 8] : P[i]) + recv;
+                    }
+                    float R[NV];
+                    if constexpr (GRP == 4) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float send = (g & 2) ? S[i] : S[i + 4];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                            R[i] = ((g & 2) ? S[i + 4] : S[i]) + recv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) R[i] = S[i];
+                    }
+                    const int q = q0 + cg + coff;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        float u = R[i] + bias;
+                        if (a.relu) u = fmaxf(u, 0.f);
+                        if (rrow) u += rv[i];
+                        u *= a.scale;
+                        if (acc_r) u += ov[i];
+                        if (a.post_div != 1.f) u = u / a.post_div;
+                        R[i] = u;
+                    }
+                    if (!(a.dbg & 8))
+#pragma unroll
+                    for (int j = 0; j < NV / 4; ++j) {
+                        const int qq = q + 4 * j;
+                        if (vec_ok && qq + 3 < a.Tout) {
+                            *reinterpret_cast<float4*>(yrow + qq) = make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = R[4 * j + e];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) { rv[i] = rn[i]; ov[i] = on[i]; }
+                }
+                tc_fence_before();
+                mbar_arrive(BAR(ACC_EMPTY + buf));
+                continue;
+            }
             const int r = rt * MROWS + lq * 32 + lane;             // GEMM row of this lane
             const bool rok = r < a.Rows;
             const int rc = rok ? r : a.Rows - 1;
@@ -419,6 +541,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
+
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) { tc3_body<1>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g2_kernel(const Tc3Args a) { tc3_body<2>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g4_kernel(const Tc3Args a) { tc3_body<4>(a); }
 
 }  // namespace tc3
 }  // namespace b200tts

@@ -38,12 +38,35 @@ struct WaveNet {
 struct Flow {
     struct Block { ConvLayer pre, post; WaveNet wn; bool odd = false; };
     b200tts_flow_config c;
+    bool fwd = false;
     std::vector<Block*> blocks;
     ~Flow();
-    int init(const b200tts_flow_config& cfg, const float* const* w, int nw);
+    int init(const b200tts_flow_config& cfg, const float* const* w, int nw, int forward_direction = 0);
     size_t workspace_bytes(int B, int T) const;
     int reverse(float* z, const float* mask, const float* g, int B, int T, void* ws, size_t ws_bytes,
                 cudaStream_t st) const;
+};
+
+struct PosteriorEnc {
+    b200tts_posterior_config c;
+    ConvLayer pre, proj;
+    WaveNet wn;
+    ~PosteriorEnc();
+    int init(const b200tts_posterior_config& cfg, const float* const* w, int nw);
+    size_t workspace_bytes(int B, int T) const;
+    int forward(const float* x, const float* mask, const float* g, const float* noise, int B, int T, float* z,
+                float* stats, void* ws, size_t ws_bytes, cudaStream_t st) const;
+};
+
+struct DurPred {
+    b200tts_duration_predictor_config c;
+    ConvLayer conv1, conv2, proj, cond, cond_lang;
+    float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+    ~DurPred();
+    int init(const b200tts_duration_predictor_config& cfg, const float* const* w, int nw);
+    size_t workspace_bytes(int B, int T) const;
+    int forward(const float* x, const float* mask, const float* g, const float* lang_emb, int B, int T, float* logw,
+                void* ws, size_t ws_bytes, cudaStream_t st) const;
 };
 
 int launch_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, const float* mask,

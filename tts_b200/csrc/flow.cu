@@ -91,8 +91,9 @@ Flow::~Flow() {
     for (auto& b : blocks) { free_conv(b->pre); free_conv(b->post); delete b; }
 }
 
-int Flow::init(const b200tts_flow_config& cfg, const float* const* w, int nw) {
+int Flow::init(const b200tts_flow_config& cfg, const float* const* w, int nw, int forward_direction) {
     c = cfg;
+    fwd = forward_direction != 0;
     B200_REQUIRE(c.channels % 2 == 0 && c.num_flows >= 1 && c.num_layers >= 1, "flow: unsupported config");
     const int per = 2 + (c.cond_channels > 0 ? 2 : 0) + 4 * c.num_layers + 2;
     B200_REQUIRE(nw == per * c.num_flows, "flow: expected %d weight tensors, got %d", per * c.num_flows, nw);
@@ -103,8 +104,9 @@ int Flow::init(const b200tts_flow_config& cfg, const float* const* w, int nw) {
     for (int n = 0; n < c.num_flows; ++n) {
         Block* b = new Block();
         blocks[n] = b;
-        // reverse pass applies flows F-1 .. 0, each after one more flip: block n sees (F - n) flips
-        b->odd = ((c.num_flows - n) % 2) == 1;
+        // reverse pass applies flows F-1 .. 0, each after one more flip: block n sees (F - n) flips;
+        // the forward pass (networks.py:223-227) flips after each block: block n sees n flips
+        b->odd = fwd ? (n % 2) == 1 : ((c.num_flows - n) % 2) == 1;
         const float* const* wn = w + (size_t)n * per;
         int rc, used = 0;
         if ((rc = pack_conv(b->pre, wn[0], wn[1], c.hidden_channels, half, 1, 1, 0, 0, b->odd ? rev.data() : nullptr,
@@ -130,6 +132,8 @@ size_t Flow::workspace_bytes(int B, int T) const {
 int Flow::reverse(float* z, const float* mask, const float* g, int B, int T, void* ws, size_t ws_bytes,
                   cudaStream_t st) const {
     B200_REQUIRE(z && mask && ws, "flow_reverse: null pointer");
+    // (also runs the forward direction when the handle was packed for it: same kernels, opposite block order,
+    //  x1 = m + x1*mask instead of x1 = (x1 - m)*mask)
     B200_REQUIRE(c.cond_channels == 0 || g != nullptr, "flow_reverse: model has cond_channels=%d but g is null",
                  c.cond_channels);
     B200_REQUIRE(ws_bytes >= workspace_bytes(B, T), "flow_reverse: workspace too small");
@@ -143,7 +147,8 @@ int Flow::reverse(float* z, const float* mask, const float* g, int B, int T, voi
     B200_REQUIRE(h && acts && out && condv, "flow_reverse: arena exhausted");
     const long long zbs = (long long)c.channels * T;
     int rc;
-    for (int n = c.num_flows - 1; n >= 0; --n) {
+    for (int step = 0; step < c.num_flows; ++step) {
+        const int n = fwd ? step : c.num_flows - 1 - step;
         const Block& b = *blocks[n];
         // logical x0 / x1 live in the upper / lower physical half when an odd number of flips is pending
         float* x0 = z + (b.odd ? (size_t)half * T : 0);
@@ -161,11 +166,81 @@ int Flow::reverse(float* z, const float* mask, const float* g, int B, int T, voi
             io.x = out; io.x_bs = (long long)H * T; io.x_cs = T; io.Tin = T;
             io.y = x1; io.y_bs = zbs; io.y_cs = T; io.Tout = T; io.B = B;
             io.ymask = mask; io.ymask_bs = T;
-            io.scale = -1.f;
+            io.scale = fwd ? 1.f : -1.f;   // forward: x1 = m + x1*mask ; reverse: x1 = (x1 - m)*mask
             io.flags = EPI_MASK_PRE | EPI_ACCUM | EPI_MASK_POST;
             if ((rc = launch_conv(b.post, io, st))) return rc;
         }
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------ posterior encoder (training / voice conversion)
+// Reference: TTS/tts/layers/vits/networks.py:275-288: pre 1x1 -> WN (16 layers) -> proj 1x1 -> z = (m + eps*exp(logs))*mask
+namespace {
+__global__ void sample_posterior_kernel(const float* stats, const float* noise, const float* mask, float* z, int C,
+                                        int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    const float m = stats[((size_t)b * 2 * C + c) * T + t];
+    const float ls = stats[((size_t)b * 2 * C + C + c) * T + t];
+    const size_t o = ((size_t)b * C + c) * T + t;
+    z[o] = __fmul_rn(__fadd_rn(m, __fmul_rn(noise[o], expf(ls))), mask[(size_t)b * T + t]);
+}
+}  // namespace
+
+PosteriorEnc::~PosteriorEnc() { free_conv(pre); free_conv(proj); }
+
+// weights: pre.w [H,Cin,1], pre.b, enc.* (WaveNet order), proj.w [2*out,H,1], proj.b
+int PosteriorEnc::init(const b200tts_posterior_config& cfg, const float* const* w, int nw) {
+    c = cfg;
+    const int expect = 2 + (c.cond_channels > 0 ? 2 : 0) + 4 * c.num_layers + 2;
+    B200_REQUIRE(nw == expect, "posterior_encoder: expected %d weight tensors, got %d", expect, nw);
+    int rc, used = 0;
+    if ((rc = pack_conv(pre, w[0], w[1], c.hidden_channels, c.in_channels, 1, 1, 0))) return rc;
+    if ((rc = wn.init(c.hidden_channels, c.kernel_size, c.dilation_rate, c.num_layers, c.cond_channels, w + 2, &used))) return rc;
+    if ((rc = pack_conv(proj, w[2 + used], w[3 + used], 2 * c.out_channels, c.hidden_channels, 1, 1, 0))) return rc;
+    pre.allow_tc = true;
+    proj.allow_tc = true;
+    return 0;
+}
+
+size_t PosteriorEnc::workspace_bytes(int B, int T) const {
+    return 3 * arena_bytes((size_t)B * c.hidden_channels * T) + arena_bytes((size_t)B * wn.cond.RowsPad + 64) + 1024;
+}
+
+int PosteriorEnc::forward(const float* x, const float* mask, const float* g, const float* noise, int B, int T, float* z,
+                          float* stats, void* ws, size_t ws_bytes, cudaStream_t st) const {
+    B200_REQUIRE(x && mask && noise && z && stats && ws, "posterior_encoder: null pointer");
+    B200_REQUIRE(c.cond_channels == 0 || g != nullptr, "posterior_encoder: model has cond_channels=%d but g is null", c.cond_channels);
+    B200_REQUIRE(ws_bytes >= workspace_bytes(B, T), "posterior_encoder: workspace too small");
+    if (B == 0 || T == 0) return 0;
+    Arena ar(ws, ws_bytes);
+    const int H = c.hidden_channels;
+    float* h = ar.f32((size_t)B * H * T);
+    float* acts = ar.f32((size_t)B * H * T);
+    float* out = ar.f32((size_t)B * H * T);
+    float* condv = ar.f32((size_t)B * wn.cond.RowsPad + 64);
+    B200_REQUIRE(h && acts && out && condv, "posterior_encoder: arena exhausted");
+    int rc;
+    {
+        ConvIO io;
+        io.x = x; io.x_bs = (long long)c.in_channels * T; io.x_cs = T; io.Tin = T;
+        io.y = h; io.y_bs = (long long)H * T; io.y_cs = T; io.Tout = T; io.B = B;
+        io.ymask = mask; io.ymask_bs = T; io.flags = EPI_MASK_POST;
+        if ((rc = launch_conv(pre, io, st))) return rc;
+    }
+    if ((rc = wn.forward(h, out, mask, g, B, T, acts, condv, st))) return rc;
+    {
+        ConvIO io;
+        io.x = out; io.x_bs = (long long)H * T; io.x_cs = T; io.Tin = T;
+        io.y = stats; io.y_bs = (long long)2 * c.out_channels * T; io.y_cs = T; io.Tout = T; io.B = B;
+        io.ymask = mask; io.ymask_bs = T; io.flags = EPI_MASK_POST;
+        if ((rc = launch_conv(proj, io, st))) return rc;
+    }
+    dim3 grid((T + 127) / 128, c.out_channels, B);
+    sample_posterior_kernel<<<grid, 128, 0, st>>>(stats, noise, mask, z, c.out_channels, T);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

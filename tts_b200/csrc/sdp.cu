@@ -190,6 +190,104 @@ __global__ void spline_inverse_kernel(float* z, const float* hp, const float* ma
 
 }  // namespace
 
+// ------------------------------------------------------------------ deterministic duration predictor (use_sdp=False)
+// Reference: TTS/tts/layers/glow_tts/duration_predictor.py:44-69 (LayerNorm eps 1e-4: generic/normalization.py:5-28)
+namespace {
+__global__ void add_chan_bias_kernel(const float* x, const float* cb, long long cb_bs, float* out, int C, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    const size_t i = ((size_t)b * C + c) * T + t;
+    out[i] = x[i] + cb[(size_t)b * cb_bs + c];
+}
+}  // namespace
+
+DurPred::~DurPred() {
+    free_conv(conv1); free_conv(conv2); free_conv(proj); free_conv(cond); free_conv(cond_lang);
+    for (float* p : {g1, b1, g2, b2}) if (p) cudaFree(p);
+}
+
+// weights: conv_1.w [F,Cin,k], .b, norm_1.gamma [1,F,1], .beta, conv_2.w [F,F,k], .b, norm_2.gamma, .beta,
+//          proj.w [1,F,1], .b, [cond.w [Cin,cond,1], .b], [cond_lang.w, .b]
+int DurPred::init(const b200tts_duration_predictor_config& cfg, const float* const* w, int nw) {
+    c = cfg;
+    const int Cin = c.in_channels + c.language_emb_dim, F = c.hidden_channels, K = c.kernel_size;
+    const int expect = 10 + (c.cond_channels > 0 ? 2 : 0) + (c.language_emb_dim > 0 ? 2 : 0);
+    B200_REQUIRE(nw == expect, "duration_predictor: expected %d weight tensors, got %d", expect, nw);
+    int rc;
+    if ((rc = pack_conv(conv1, w[0], w[1], F, Cin, K, 1, K / 2))) return rc;
+    if ((rc = upload(&g1, w[2], F))) return rc;
+    if ((rc = upload(&b1, w[3], F))) return rc;
+    if ((rc = pack_conv(conv2, w[4], w[5], F, F, K, 1, K / 2))) return rc;
+    if ((rc = upload(&g2, w[6], F))) return rc;
+    if ((rc = upload(&b2, w[7], F))) return rc;
+    if ((rc = pack_conv(proj, w[8], w[9], 1, F, 1, 1, 0))) return rc;
+    int i = 10;
+    if (c.cond_channels > 0) { if ((rc = pack_conv(cond, w[i], w[i + 1], Cin, c.cond_channels, 1, 1, 0))) return rc; i += 2; }
+    if (c.language_emb_dim > 0) { if ((rc = pack_conv(cond_lang, w[i], w[i + 1], Cin, c.language_emb_dim, 1, 1, 0))) return rc; }
+    return 0;
+}
+
+size_t DurPred::workspace_bytes(int B, int T) const {
+    const int Cin = c.in_channels + c.language_emb_dim;
+    return arena_bytes((size_t)B * Cin * T) + 2 * arena_bytes((size_t)B * c.hidden_channels * T) +
+           arena_bytes((size_t)B * std::max(std::max(cond.RowsPad, cond_lang.RowsPad), 64) + 64) + 1024;
+}
+
+int DurPred::forward(const float* x, const float* mask, const float* g, const float* lang_emb, int B, int T,
+                     float* logw, void* ws, size_t ws_bytes, cudaStream_t st) const {
+    B200_REQUIRE(x && mask && logw && ws, "duration_predictor: null pointer");
+    B200_REQUIRE(ws_bytes >= workspace_bytes(B, T), "duration_predictor: workspace too small");
+    if (B == 0 || T == 0) return 0;
+    const int Cin = c.in_channels + c.language_emb_dim, F = c.hidden_channels;
+    Arena ar(ws, ws_bytes);
+    float* xin = ar.f32((size_t)B * Cin * T);
+    float* h1 = ar.f32((size_t)B * F * T);
+    float* h2 = ar.f32((size_t)B * F * T);
+    const int cpad = std::max(std::max(cond.RowsPad, cond_lang.RowsPad), 64);
+    float* cv = ar.f32((size_t)B * cpad + 64);
+    B200_REQUIRE(xin && h1 && h2 && cv, "duration_predictor: arena exhausted");
+    int rc;
+    const float* cur = x;
+    const bool has_g = c.cond_channels > 0 && g, has_l = c.language_emb_dim > 0 && lang_emb;
+    if (has_g || has_l) {       // x = x + cond(g) (+ cond_lang(lang_emb)) : per-utterance channel bias on the INPUT
+        bool first = true;
+        if (has_g) {
+            ConvIO io;
+            io.x = g; io.x_bs = c.cond_channels; io.x_cs = 1; io.Tin = 1;
+            io.y = cv; io.y_bs = cpad; io.y_cs = 1; io.Tout = 1; io.B = B;
+            if ((rc = launch_conv(cond, io, st))) return rc;
+            first = false;
+        }
+        if (has_l) {
+            ConvIO io;
+            io.x = lang_emb; io.x_bs = c.language_emb_dim; io.x_cs = 1; io.Tin = 1;
+            io.y = cv; io.y_bs = cpad; io.y_cs = 1; io.Tout = 1; io.B = B;
+            if (!first) io.flags = EPI_ACCUM;
+            if ((rc = launch_conv(cond_lang, io, st))) return rc;
+        }
+        dim3 grid((T + 127) / 128, Cin, B);
+        add_chan_bias_kernel<<<grid, 128, 0, st>>>(x, cv, cpad, xin, Cin, T);
+        count_launch();
+        B200_CUDA_OK(cudaGetLastError());
+        cur = xin;
+    }
+    auto conv_relu = [&](const ConvLayer& L, const float* in, int cin, float* out) {
+        ConvIO io;
+        io.x = in; io.x_bs = (long long)cin * T; io.x_cs = T; io.Tin = T; io.xmask = mask; io.xmask_bs = T;
+        io.y = out; io.y_bs = (long long)F * T; io.y_cs = T; io.Tout = T; io.B = B; io.act = ACT_RELU;
+        return launch_conv(L, io, st);
+    };
+    if ((rc = conv_relu(conv1, cur, Cin, h1))) return rc;
+    if ((rc = launch_add_layernorm(h1, nullptr, g1, b1, nullptr, h1, B, F, T, 1e-4f, st))) return rc;
+    if ((rc = conv_relu(conv2, h1, F, h2))) return rc;
+    if ((rc = launch_add_layernorm(h2, nullptr, g2, b2, nullptr, h2, B, F, T, 1e-4f, st))) return rc;
+    ConvIO io;
+    io.x = h2; io.x_bs = (long long)F * T; io.x_cs = T; io.Tin = T; io.xmask = mask; io.xmask_bs = T;
+    io.y = logw; io.y_bs = T; io.y_cs = T; io.Tout = T; io.B = B;
+    io.ymask = mask; io.ymask_bs = T; io.flags = EPI_MASK_POST;
+    return launch_conv(proj, io, st);
+}
+
 DDSConv::~DDSConv() {
     for (auto& l : conv1x1) free_conv(l);
     for (float* p : dev) if (p) cudaFree(p);

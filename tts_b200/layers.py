@@ -7,9 +7,11 @@ sub-modules are parameter containers only -- their ``forward`` is never called) 
   TextEncoder                  <- TTS/tts/layers/vits/networks.py:29-100
   ResidualCouplingBlocks       <- TTS/tts/layers/vits/networks.py:169-232   (reverse=True)
   StochasticDurationPredictor  <- TTS/tts/layers/vits/stochastic_duration_predictor.py:150-294 (reverse=True)
-  PosteriorEncoder             <- TTS/tts/layers/vits/networks.py:235-288   (parameters only: training / VC)
+  ResidualCouplingBlocks       <- ... :223-227 (reverse=False, no log-det: the voice-conversion direction)
+  PosteriorEncoder             <- TTS/tts/layers/vits/networks.py:235-288   (voice conversion)
+  DurationPredictor            <- TTS/tts/layers/glow_tts/duration_predictor.py:22-69 (VitsArgs.use_sdp=False)
 
-Training-direction calls raise NotImplementedError: this package is the inference hot path.
+Training-only calls (SDP forward / likelihoods) raise NotImplementedError: this package is the inference hot path.
 """
 import ctypes
 import math
@@ -154,19 +156,34 @@ class ResidualCouplingBlocks(EngineModule):
             ResidualCouplingBlock(channels, hidden_channels, kernel_size, dilation_rate, num_layers,
                                   cond_channels=cond_channels, mean_only=True) for _ in range(num_flows)])
 
-    def _create(self, device):
+    def _create(self, device, forward_direction=False):
         cfg = _lib.FlowConfigC(self.channels, self.hidden_channels, self.kernel_size, self.dilation_rate,
                                self.num_layers, self.num_flows, self.cond_channels)
         tensors = []
         for f in self.flows:
             tensors += _wb(f.pre) + f.enc.ordered_weights() + _wb(f.post)
-        return self._make("b200tts_flow_create", cfg, tensors)
+        return self._make("b200tts_flow_create_forward" if forward_direction else "b200tts_flow_create", cfg, tensors)
+
+    def _drop_handle(self):
+        super()._drop_handle()
+        h = self.__dict__.get("_handle_fwd", None)
+        if h is not None:
+            _lib.lib().b200tts_flow_destroy(h)
+        self._handle_fwd = None
+
+    def _forward_handle(self, device):
+        if self.__dict__.get("_handle_fwd", None) is None or self._handle_fwd_device != device:
+            self._drop_handle()
+            with torch.cuda.device(device):
+                self._handle_fwd = self._create(device, forward_direction=True)
+            self._handle_fwd_device = device
+        return self._handle_fwd
 
     @torch.no_grad()
     def forward(self, x, x_mask, g=None, reverse=False):
-        """x [B,C,T], x_mask [B,1,T], g [B,cond,1] -> z [B,C,T]   (networks.py:214-232, reverse branch)."""
-        if not reverse:
-            raise NotImplementedError("tts_b200: the flow is implemented for inference (reverse=True) only")
+        """x [B,C,T], x_mask [B,1,T], g [B,cond,1] -> z [B,C,T]   (networks.py:214-232).
+        reverse=True is the synthesis direction; reverse=False the posterior->prior direction used by voice
+        conversion (the per-block log-determinant the reference discards at :226 is not computed)."""
         _lib.require_cuda(x, "x")
         if self.cond_channels > 0 and g is None:
             raise ValueError("tts_b200.ResidualCouplingBlocks: cond_channels > 0 but g is None")
@@ -179,30 +196,142 @@ class ResidualCouplingBlocks(EngineModule):
         mask = torch.zeros((b, 1, t), dtype=torch.float32, device=x.device)
         mask[:, :, :t_in] = x_mask
         gl = None if self.cond_channels == 0 else g.to(torch.float32).contiguous()
-        h = self.handle(z.device)
+        h = self.handle(z.device) if reverse else self._forward_handle(z.device)
         L = _lib.lib()
         with torch.cuda.device(z.device):
             ws = _lib.workspace(z.device, L.b200tts_flow_workspace_bytes(h, b, t), "flow")
             rc = L.b200tts_flow_reverse(h, _lib.ptr(z), _lib.ptr(mask), _lib.ptr(gl), b, t, _lib.ptr(ws),
                                         ctypes.c_size_t(ws.numel()), _lib.stream_ptr(z.device))
-        _lib.check(rc, "flow_reverse")
+        _lib.check(rc, "flow_reverse" if reverse else "flow_forward")
+        if self.num_flows % 2:  # the channel flips are folded into the packed weights; an odd count leaves one over
+            z = torch.flip(z, [1])
         return z if t == t_in else z[:, :, :t_in].contiguous()
 
 
-class PosteriorEncoder(nn.Module):
-    """Parameters of TTS/tts/layers/vits/networks.py:235-273 (used by training / voice conversion)."""
+class PosteriorEncoder(EngineModule):
+    """TTS/tts/layers/vits/networks.py:235-288 (voice conversion / the encoder half of training)."""
+
+    _destroy = "b200tts_posterior_destroy"
 
     def __init__(self, in_channels, out_channels, hidden_channels, kernel_size, dilation_rate, num_layers,
                  cond_channels=0):
         super().__init__()
         self.in_channels, self.out_channels, self.hidden_channels = in_channels, out_channels, hidden_channels
+        self.kernel_size, self.dilation_rate, self.num_layers = kernel_size, dilation_rate, num_layers
+        self.cond_channels = int(cond_channels or 0)
         self.pre = nn.Conv1d(in_channels, hidden_channels, 1)
         self.enc = WN(hidden_channels, hidden_channels, kernel_size, dilation_rate, num_layers,
                       c_in_channels=cond_channels)
         self.proj = nn.Conv1d(hidden_channels, out_channels * 2, 1)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("tts_b200: PosteriorEncoder (training / voice conversion) is outside round 1")
+    def _create(self, device):
+        cfg = _lib.PosteriorConfigC(self.in_channels, self.out_channels, self.hidden_channels, self.kernel_size,
+                                    self.dilation_rate, self.num_layers, self.cond_channels)
+        return self._make("b200tts_posterior_create", cfg, _wb(self.pre) + self.enc.ordered_weights() + _wb(self.proj))
+
+    @torch.no_grad()
+    def forward(self, x, x_lengths, g=None, noise=None):
+        """x [B,C,T] (linear spectrogram), x_lengths [B], g [B,cond,1] -> (z, mean, log_scale, x_mask)
+        (networks.py:275-288).  ``noise`` [B,out,T] may be supplied; by default it is drawn on the device like
+        the reference's ``torch.randn_like(mean)``."""
+        _lib.require_cuda(x, "x")
+        dev = x.device
+        b, _, t_in = x.shape
+        t = (t_in + 3) // 4 * 4            # 16-byte aligned rows for the tensor-core kernel (extra frames are masked)
+        xs = torch.zeros((b, self.in_channels, t), dtype=torch.float32, device=dev)
+        xs[:, :, :t_in] = x
+        lens = x_lengths.to(dev)
+        mask = (torch.arange(t, device=dev)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(1).contiguous()
+        if noise is None:
+            noise = torch.randn((b, self.out_channels, t_in), dtype=torch.float32, device=dev)
+        ns = torch.zeros((b, self.out_channels, t), dtype=torch.float32, device=dev)
+        ns[:, :, :t_in] = noise.to(device=dev, dtype=torch.float32)
+        if self.cond_channels > 0 and g is None:
+            raise ValueError("tts_b200.PosteriorEncoder: cond_channels > 0 but g is None")
+        gl = None if self.cond_channels == 0 else g.to(torch.float32).reshape(b, self.cond_channels).contiguous()
+        z = torch.empty((b, self.out_channels, t), dtype=torch.float32, device=dev)
+        stats = torch.empty((b, 2 * self.out_channels, t), dtype=torch.float32, device=dev)
+        h = self.handle(dev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, L.b200tts_posterior_workspace_bytes(h, b, t), "posterior")
+            rc = L.b200tts_posterior_forward(h, _lib.ptr(xs), _lib.ptr(mask), _lib.ptr(gl), _lib.ptr(ns), b, t,
+                                             _lib.ptr(z), _lib.ptr(stats), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                             _lib.stream_ptr(dev))
+        _lib.check(rc, "posterior_forward")
+        o = self.out_channels
+        return (z[:, :, :t_in].contiguous(), stats[:, :o, :t_in].contiguous(), stats[:, o:, :t_in].contiguous(),
+                mask[:, :, :t_in].contiguous())
+
+
+class _LayerNorm1(nn.Module):
+    """Parameters of TTS/tts/layers/generic/normalization.py:5-28 (gamma/beta shaped [1,C,1], eps 1e-4)."""
+
+    def __init__(self, channels, eps=1e-4):
+        super().__init__()
+        self.channels, self.eps = channels, eps
+        self.gamma = nn.Parameter(torch.ones(1, channels, 1) * 0.1)
+        self.beta = nn.Parameter(torch.zeros(1, channels, 1))
+
+
+class DurationPredictor(EngineModule):
+    """TTS/tts/layers/glow_tts/duration_predictor.py:22-69 -- the deterministic predictor VITS builds when
+    ``use_sdp=False`` (vits.py:646-654): conv-relu-LN-(dropout) x2 -> 1x1 projection to log-durations."""
+
+    _destroy = "b200tts_duration_predictor_destroy"
+
+    def __init__(self, in_channels, hidden_channels, kernel_size, dropout_p, cond_channels=None,
+                 language_emb_dim=None):
+        super().__init__()
+        self._lang = int(language_emb_dim or 0)
+        self._cond = int(cond_channels or 0)
+        self._in = in_channels
+        cin = in_channels + self._lang
+        self.in_channels, self.filter_channels, self.kernel_size = cin, hidden_channels, kernel_size
+        self.conv_1 = nn.Conv1d(cin, hidden_channels, kernel_size, padding=kernel_size // 2)
+        self.norm_1 = _LayerNorm1(hidden_channels)
+        self.conv_2 = nn.Conv1d(hidden_channels, hidden_channels, kernel_size, padding=kernel_size // 2)
+        self.norm_2 = _LayerNorm1(hidden_channels)
+        self.proj = nn.Conv1d(hidden_channels, 1, 1)
+        if self._cond:
+            self.cond = nn.Conv1d(self._cond, cin, 1)
+        if self._lang:
+            self.cond_lang = nn.Conv1d(self._lang, cin, 1)
+
+    def _create(self, device):
+        cfg = _lib.DurationPredictorConfigC(self._in, self.filter_channels, self.kernel_size, self._cond, self._lang)
+        tensors = _wb(self.conv_1) + [_host(self.norm_1.gamma.reshape(-1)), _host(self.norm_1.beta.reshape(-1))]
+        tensors += _wb(self.conv_2) + [_host(self.norm_2.gamma.reshape(-1)), _host(self.norm_2.beta.reshape(-1))]
+        tensors += _wb(self.proj)
+        if self._cond:
+            tensors += _wb(self.cond)
+        if self._lang:
+            tensors += _wb(self.cond_lang)
+        return self._make("b200tts_duration_predictor_create", cfg, tensors)
+
+    @torch.no_grad()
+    def forward(self, x, x_mask, g=None, lang_emb=None):
+        """x [B,C,T], x_mask [B,1,T], g [B,cond,1], lang_emb [B,L,1] -> log-durations [B,1,T]."""
+        _lib.require_cuda(x, "x")
+        dev = x.device
+        x = x.to(torch.float32).contiguous()
+        b, cin, t = x.shape
+        if cin != self.in_channels:
+            raise ValueError(f"tts_b200.DurationPredictor: expected {self.in_channels} input channels, got {cin}")
+        mask = x_mask.to(torch.float32).expand(b, 1, t).contiguous()
+        gl = g.to(torch.float32).reshape(b, self._cond).contiguous() if (self._cond and g is not None) else None
+        ll = lang_emb.to(torch.float32).reshape(b, self._lang).contiguous() \
+            if (self._lang and lang_emb is not None) else None
+        logw = torch.empty((b, 1, t), dtype=torch.float32, device=dev)
+        h = self.handle(dev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            ws = _lib.workspace(dev, L.b200tts_duration_predictor_workspace_bytes(h, b, t), "duration_predictor")
+            rc = L.b200tts_duration_predictor_forward(h, _lib.ptr(x), _lib.ptr(mask), _lib.ptr(gl), _lib.ptr(ll), b, t,
+                                                      _lib.ptr(logw), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                                      _lib.stream_ptr(dev))
+        _lib.check(rc, "duration_predictor_forward")
+        return logw
 
 
 # ----------------------------------------------------------------------------- text encoder

@@ -17,7 +17,7 @@ from torch import nn
 
 from . import _lib
 from .hifigan import HifiganGenerator
-from .layers import (EngineModule, PosteriorEncoder, ResidualCouplingBlocks, StochasticDurationPredictor,
+from .layers import (DurationPredictor, EngineModule, PosteriorEncoder, ResidualCouplingBlocks, StochasticDurationPredictor,
                      TextEncoder, durations_to_path, expand_prior)
 
 
@@ -198,8 +198,10 @@ class Vits(nn.Module):
                 a.hidden_channels, 192, 3, a.dropout_p_duration_predictor, 4,
                 cond_channels=self.embedded_speaker_dim if a.condition_dp_on_speaker else 0,
                 language_emb_dim=self.embedded_language_dim)
-        else:
-            raise NotImplementedError("tts_b200: use_sdp=False (deterministic DurationPredictor) is not built yet")
+        else:  # vits.py:646-654
+            self.duration_predictor = DurationPredictor(
+                a.hidden_channels, 256, 3, a.dropout_p_duration_predictor,
+                cond_channels=self.embedded_speaker_dim, language_emb_dim=self.embedded_language_dim)
         self.waveform_decoder = HifiganGenerator(
             a.hidden_channels, 1, a.resblock_type_decoder, a.resblock_dilation_sizes_decoder,
             a.resblock_kernel_sizes_decoder, a.upsample_kernel_sizes_decoder, a.upsample_initial_channel_decoder,
@@ -285,8 +287,10 @@ class Vits(nn.Module):
         _lib.require_cuda(x, "x")
         a = self.args
         sid, g, lid, durations = self._set_cond_input(aux_input)
-        if durations is not None:
-            raise NotImplementedError("tts_b200: externally supplied durations (vits.py:1141-1143) are not built")
+        if durations is not None:  # vits.py:1141-1143: w = durations.unsqueeze(0), i.e. a single utterance
+            assert durations.shape[-1] == x.shape[-1]
+            if x.shape[0] != 1:
+                raise ValueError("tts_b200.Vits: aux_input['durations'] is defined for batch size 1 (vits.py:1143)")
         x_lengths = self._set_x_lengths(x, aux_input)
         if a.use_speaker_embedding and sid is not None:
             g = self.emb_g(sid.to(x.device)).unsqueeze(-1)
@@ -299,10 +303,21 @@ class Vits(nn.Module):
         with _Stage(self, "text_encoder"):
             h, stats, x_mask = self.text_encoder.forward_stats(x, x_lengths, lang_emb=lang_emb)
         with _Stage(self, "duration_predictor"):
-            logw = self.duration_predictor(h, x_mask, g=g if a.condition_dp_on_speaker else None, reverse=True,
-                                           noise_scale=self.inference_noise_scale_dp, lang_emb=lang_emb,
-                                           noise=sdp_noise)
-            w_ceil, cum, y_lengths = durations_to_path(logw, x_mask, float(self.length_scale))
+            logw = None
+            if durations is not None:
+                w = durations.to(device=x.device, dtype=torch.float32).reshape(1, 1, -1)
+                w_ceil = torch.ceil(w)
+                cum = torch.cumsum(w_ceil.reshape(1, -1), dim=1)
+                y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+            else:
+                if a.use_sdp:
+                    logw = self.duration_predictor(h, x_mask, g=g if a.condition_dp_on_speaker else None,
+                                                   reverse=True, noise_scale=self.inference_noise_scale_dp,
+                                                   lang_emb=lang_emb, noise=sdp_noise)
+                else:
+                    logw = self.duration_predictor(h, x_mask, g=g if a.condition_dp_on_speaker else None,
+                                                   lang_emb=lang_emb)
+                w_ceil, cum, y_lengths = durations_to_path(logw, x_mask, float(self.length_scale))
         # the one host sync of the path: T_dec = max(y_lengths) (sequence_mask(y_lengths, None), helpers.py:53-54)
         t_dec = int(y_lengths.max().item())
         flag = getattr(self.duration_predictor, "last_error_flag", None)
@@ -329,8 +344,51 @@ class Vits(nn.Module):
         return {"model_outputs": o, "alignments": attn, "durations": w_ceil, "z": z, "z_p": z_p, "m_p": m_p,
                 "logs_p": logs_p, "y_mask": y_mask, "y_lengths": y_lengths, "logw": logw}
 
+    # ------------------------------------------------------------------ voice conversion (vits.py:1175-1232)
+    @torch.no_grad()
+    def inference_voice_conversion(self, reference_wav, speaker_id=None, d_vector=None, reference_speaker_id=None,
+                                   reference_d_vector=None, *, posterior_noise=None):
+        """reference_wav [B,1,T] or [B,T] (CUDA) -> converted waveform [B,1,T'] (vits.py:1175-1198)."""
+        from .audio import wav_to_spec
+        au = _get(self.config, "audio")
+        if reference_wav.dim() == 2:
+            reference_wav = reference_wav.unsqueeze(1)
+        y = wav_to_spec(reference_wav, au.fft_size, au.hop_length, au.win_length, center=False)
+        y_lengths = torch.tensor([y.size(-1)] * y.size(0)).to(y.device)
+        speaker_cond_src = reference_speaker_id if reference_speaker_id is not None else reference_d_vector
+        speaker_cond_tgt = speaker_id if speaker_id is not None else d_vector
+        wav, _, _ = self.voice_conversion(y, y_lengths, speaker_cond_src, speaker_cond_tgt,
+                                          posterior_noise=posterior_noise)
+        return wav
+
+    @torch.no_grad()
+    def voice_conversion(self, y, y_lengths, speaker_cond_src, speaker_cond_tgt, *, posterior_noise=None):
+        """y [B,C,T] linear spectrograms -> (o_hat, y_mask, (z, z_p, z_hat))   (vits.py:1200-1232).
+        ``posterior_noise`` [B,H,T] replaces the posterior encoder's randn_like draw (networks.py:287)."""
+        assert self.num_speakers > 0, "num_speakers have to be larger than 0."
+        _lib.require_cuda(y, "y")
+        a = self.args
+        if a.use_speaker_embedding and not a.use_d_vector_file:
+            ids = lambda v: torch.as_tensor(v, dtype=torch.int64, device=y.device).reshape(-1)
+            g_src = self.emb_g(ids(speaker_cond_src)).unsqueeze(-1)
+            g_tgt = self.emb_g(ids(speaker_cond_tgt)).unsqueeze(-1)
+        elif not a.use_speaker_embedding and a.use_d_vector_file:
+            g_src = F.normalize(speaker_cond_src.to(y.device)).unsqueeze(-1)
+            g_tgt = F.normalize(speaker_cond_tgt.to(y.device)).unsqueeze(-1)
+        else:
+            raise RuntimeError(" [!] Voice conversion is only supported on multi-speaker models.")
+        with _Stage(self, "posterior_encoder"):
+            z, _, _, y_mask = self.posterior_encoder(y, y_lengths, g=g_src, noise=posterior_noise)
+        with _Stage(self, "flow"):
+            z_p = self.flow(z, y_mask, g=g_src)
+            z_hat = self.flow(z_p, y_mask, g=g_tgt, reverse=True)
+        with _Stage(self, "waveform_decoder"):
+            o_hat = self.waveform_decoder(z_hat * y_mask, g=g_tgt)
+        return o_hat, y_mask, (z, z_p, z_hat)
+
     def forward(self, *args, **kwargs):
-        raise NotImplementedError("tts_b200.Vits implements the inference path only (use .inference)")
+        raise NotImplementedError("tts_b200.Vits implements the inference paths only "
+                                  "(.inference, .voice_conversion); training is out of scope")
 
     # ------------------------------------------------------------------ checkpoints (vits.py:1698-1725)
     def load_checkpoint(self, config, checkpoint_path, eval=False, strict=True, cache=False):  # pylint: disable=redefined-builtin
