@@ -137,14 +137,12 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
             a3.n_ttiles = (T + a3.tstep - 1) / a3.tstep; a3.n_rtiles = 1;
         }
         smem2 = smem_bytes3(a3.rows_pad, a3.raw_w);
-        CK(cudaFuncSetAttribute(conv1d_tc3g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CK(cudaFuncSetAttribute(conv1d_tc3g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (G > 1) CK(cudaFuncSetAttribute(grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         const int tiles = a3.B * a3.n_ttiles * a3.n_rtiles;
         grid2 = dim3(tiles < sms ? tiles : sms);
-        if (G == 2) conv1d_tc3g2_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
-        else if (G == 4) conv1d_tc3g4_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        if (G > 1) grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         else conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
     } else if (v2) {
         using namespace b200tts::tc2;
@@ -182,8 +180,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (getenv("TC_TRACE") && v3) {
         unsigned long long* dtr; CK(cudaMalloc(&dtr, (size_t)grid2.x * 32 * 8)); CK(cudaMemset(dtr, 0, (size_t)grid2.x * 32 * 8));
         a3.trace = dtr;
-        if (G == 2) b200tts::tc3::conv1d_tc3g2_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
-        else if (G == 4) b200tts::tc3::conv1d_tc3g4_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        if (G > 1) b200tts::tc3::grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         else b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         CK(cudaDeviceSynchronize());
         std::vector<unsigned long long> tr((size_t)grid2.x * 32);
@@ -231,7 +228,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (iters > 0 && herr == 0 && !accum) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        for (int i = 0; i < iters; ++i) { if (v3 && G == 2) b200tts::tc3::conv1d_tc3g2_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3 && G == 4) b200tts::tc3::conv1d_tc3g4_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
+        for (int i = 0; i < iters; ++i) { if (v3 && G > 1) b200tts::tc3::grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
         printf("  %.3f ms  %.1f TFLOP/s (algorithmic fp32)", ms, 2.0 * B * Cout * (double)C * K * T / ms / 1e9);
@@ -254,6 +251,10 @@ int main(int argc, char** argv) {
     fails += run_case(3, 32, 996, 11, 5, 1, 0, 0);
     fails += run_case(2, 32, 2000, 7, 1, 1, 1, 0);
     fails += run_case(2, 32, 480, 3, 3, 0, 0, 0);
+    fails += run_case(2, 32, 724, 3, 5, 1, 0, 0);
+    fails += run_case(2, 64, 724, 3, 3, 1, 0, 0);
+    fails += run_case(2, 64, 500, 7, 1, 0, 1, 0);
+    fails += run_case(2, 32, 500, 5, 2, 0, 1, 0);      // generic (runtime dilation) grouped epilogue
     if (fails == 0 || (argc > 1 && !strcmp(argv[1], "time"))) {
         run_case(32, 128, 9600, 11, 5, 1, 0, 5);       // HiFiGAN stage 1 at cfg2
         run_case(32, 128, 9600, 3, 1, 1, 0, 5);

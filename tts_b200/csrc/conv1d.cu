@@ -514,6 +514,57 @@ int pack_conv_transpose(ConvLayer& L, const float* w, const float* bias, int Cin
     return pack_rows(L, Wl, bl, rows, Cin, K);
 }
 
+// ------------------------------------------------------------------ single-output-row conv (HiFiGAN conv_post)
+// y[b, 0, t] = act(bias + sum_ci sum_k w[ci, k] * lrelu(x[b, ci, t + k - pad])), K taps, dilation 1.  One output row has
+// no reuse across rows, so this is a pure streaming kernel: each thread owns four consecutive samples and reads its
+// window as aligned float4 (neighbouring threads' overlaps are L1 hits), 4*K FMAs per channel.  HBM-bound by the x read
+// (Cin * 4 B per output sample).  Reference: hifigan_generator.py:262-264.
+template <int K>
+__global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restrict__ x, long long x_bs, int x_cs, int Cin,
+                                                          int T, const float* __restrict__ w, int w_stride,
+                                                          const float* __restrict__ bias, float slope, int act,
+                                                          float* __restrict__ y, long long y_bs) {
+    constexpr int PAD = (K - 1) / 2, NL = (4 + 4 + (K - 1 - PAD) + 3) / 4;   // float4 loads covering [t0 - 4, t0 + 4 + K-1-PAD)
+    extern __shared__ float ws[];
+    for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) ws[i] = w[(size_t)i * w_stride];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (t0 >= T) return;
+    const float* xb = x + b * x_bs + t0;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int ci = 0; ci < Cin; ++ci) {
+        const float* xr = xb + (long long)ci * x_cs;
+        float win[4 * NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const int t = t0 - 4 + 4 * l;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // T % 4 == 0: all in or all out
+            win[4 * l] = v.x; win[4 * l + 1] = v.y; win[4 * l + 2] = v.z; win[4 * l + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * NL; ++i) win[i] = win[i] > 0.f ? win[i] : win[i] * slope;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float wk = ws[ci * K + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(wk, win[4 - PAD + j + k], acc[j]);
+        }
+    }
+    const float bv = bias[0];
+    float4 o;
+    float* po = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float u = acc[j] + bv;
+        if (act == ACT_TANH) u = tanhf(u);
+        po[j] = u;
+    }
+    *reinterpret_cast<float4*>(y + b * y_bs + t0) = o;
+}
+
 // ------------------------------------------------------------------ host: launch
 template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI>
 static int launch_variant(const ConvKArgs& ka, int B, int RowsPad, cudaStream_t st) {
@@ -556,6 +607,24 @@ static int launch_cic(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaS
 
 // tcgen05 path: returns -1 when the layer / shape / epilogue is not eligible (caller falls through to the FMA kernel)
 static int* g_tc_err = nullptr;
+
+// launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains (the kernel
+// itself waits with griddepcontrol.wait before touching activations).  B200TTS_NO_PDL=1 restores plain launches.
+static cudaError_t launch_tc3(tc3::Tc3Kernel k, int grid, size_t smem, cudaStream_t st, const tc3::Tc3Args& t) {
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("B200TTS_NO_PDL"); pdl = (e && atoi(e)) ? 0 : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc3::NTHREADS2);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, t);
+}
 static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
     static int enabled = -1, v2_enabled = -1, grouped_enabled = 1, num_sms = 0;
     if (enabled < 0) {
@@ -574,8 +643,9 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc2::conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3g2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int g : {2, 4})
+            for (int d : {0, 1, 3, 5})
+                B200_CUDA_OK(cudaFuncSetAttribute(tc3::grouped_kernel(g, d), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaMalloc((void**)&g_tc_err, sizeof(int)));
         B200_CUDA_OK(cudaMemset(g_tc_err, 0, sizeof(int)));
         int dev = 0;
@@ -609,8 +679,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             t.err = g_tc_err;
             const long long tiles = (long long)t.B * t.n_ttiles;
             const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-            if (G == 2) tc3::conv1d_tc3g2_kernel<<<grid, tc3::NTHREADS2, tc3::smem_bytes3(rp, rp + 4), st>>>(t);
-            else tc3::conv1d_tc3g4_kernel<<<grid, tc3::NTHREADS2, tc3::smem_bytes3(rp, rp + 4), st>>>(t);
+            B200_CUDA_OK(launch_tc3(tc3::grouped_kernel(G, L.dil), grid, tc3::smem_bytes3(rp, rp + 4), st, t));
             count_launch();
             B200_CUDA_OK(cudaGetLastError());
             return 0;
@@ -638,7 +707,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         t.err = g_tc_err;
         const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
         const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-        tc3::conv1d_tc3_kernel<<<grid, tc3::NTHREADS2, tc3::smem_bytes3(rows_pad, rows_pad + 4), st>>>(t);
+        B200_CUDA_OK(launch_tc3(tc3::conv1d_tc3_kernel, grid, tc3::smem_bytes3(rows_pad, rows_pad + 4), st, t));
         count_launch();
         B200_CUDA_OK(cudaGetLastError());
         return 0;
@@ -725,6 +794,20 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     if (a.act == ACT_TANH) {
         B200_REQUIRE(L.ups == 1 && !io.res && !io.cond && a.flags == 0 && a.scale == 1.f && a.post_div == 1.f,
                      "launch_conv: tanh epilogue takes no other options");
+        // conv_post (one output row, 7 taps): streaming kernel when rows are 16-byte aligned
+        if (L.Rows == 1 && L.K == 7 && L.dil == 1 && L.pad == 3 && !a.xmask && a.Tin == a.Tout && (a.Tout % 4) == 0 &&
+            (a.x_cs % 4) == 0 && (a.x_bs % 4) == 0 && (a.y_bs % 4) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && (size_t)L.Cin * L.K * 4 <= 48 * 1024) {
+            dim3 grid((a.Tout / 4 + 255) / 256, io.B);
+            if (grid.y <= 65535) {
+                conv1d_row1_kernel<7><<<grid, 256, (size_t)L.Cin * L.K * 4, st>>>(a.x, a.x_bs, a.x_cs, L.Cin, a.Tout, L.w,
+                                                                                 L.co_tile, L.bias, a.in_slope, a.act, a.y,
+                                                                                 a.y_bs);
+                count_launch();
+                B200_CUDA_OK(cudaGetLastError());
+                return 0;
+            }
+        }
         return launch_cic<KEPI_TANH>(a, L.co_tile, io.B, L.RowsPad, st);
     }
     if (int rc = try_launch_tc(L, io, a, st); rc != -1) return rc;

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "conv_tc.cuh"   // descriptor / barrier helpers
 
 namespace b200tts {
@@ -34,9 +36,18 @@ using namespace tc;       // smem_u32, mbar_*, make_desc, make_idesc, mma_tf32, 
 constexpr int TT2 = 256;          // time steps per tile = MMA N
 constexpr int MROWS = 128;        // output rows per tile = MMA M (weight rows are zero padded up to it)
 constexpr int KC2 = 8;            // input channels per chunk (2 slabs, one MMA k-step)
-constexpr int NRAW = 4;           // raw (cp.async) ring depth
-constexpr int NA2 = 3;            // transformed activation stages
-constexpr int NB2 = 10;           // weight ring depth (one 8 KB tap block per slot)
+#ifndef TC3_NRAW
+#define TC3_NRAW 4
+#endif
+#ifndef TC3_NA2
+#define TC3_NA2 3
+#endif
+#ifndef TC3_NB2
+#define TC3_NB2 10
+#endif
+constexpr int NRAW = TC3_NRAW;    // raw (cp.async) ring depth
+constexpr int NA2 = TC3_NA2;      // transformed activation stages
+constexpr int NB2 = TC3_NB2;      // weight ring depth (one 8 KB tap block per slot)
 constexpr int NTHREADS2 = 448;    // warps 0-3 + 10-13 epilogue, 4-7 producers, 8 loader, 9 MMA
 constexpr int NPROD = 128;
 
@@ -75,13 +86,34 @@ static inline size_t smem_bytes3(int rows_pad, int raw_w) {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// tcgen05.ld without the wait: issue several, then one tmem_wait_ld() (the loads' latencies overlap)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t* r) {   // N = 1, 2, 4, 8 or 16 columns
+    if constexpr (N == 16) tmem_ld16_nowait(taddr, r);
+    else if constexpr (N == 8)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    else if constexpr (N == 4)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    else if constexpr (N == 2)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+    else
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 #define TC3_STAMP(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime(); } while (0)
 
 constexpr int TSTEP_GROUPED = 240;   // 15 chunks of 16 columns: leaves room for the (GRP-1)*dil <= 15 column shift
 
-template <int GRP>
+template <int GRP, int DIL>   // DIL > 0: the layer's dilation as a compile-time constant (windowed TMEM reads in the grouped epilogue)
 __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,9 +138,9 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     const uint32_t ncols = 512;
 
     if (tid == 0) {
-        for (int i = 0; i < NA2; ++i) { mbar_init(BAR(A_FULL + i), NPROD); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < NA2; ++i) { mbar_init(BAR(A_FULL + i), NPROD / 32); mbar_init(BAR(A_EMPTY + i), 1); }
         for (int i = 0; i < NB2; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 256); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -120,6 +152,11 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) TC3_STAMP(0);
+    // Programmatic dependent launch: the next layer's CTAs may take SMs as this grid drains (they park in their own
+    // griddepcontrol.wait); every role that touches activations waits for the previous layer here.  The weight loader
+    // (warp 8) reads only constants and starts filling its ring at once.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp != 8) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     auto decode = [&](int it, int& b, int& rt, int& q0) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -220,7 +257,8 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             }
             }
             fence_async_smem();
-            mbar_arrive(BAR(A_FULL + as));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(A_FULL + as));       // one arrival per producer warp
             if (ptid == 0) { if (g == 0) TC3_STAMP(1); if (g == nchunks - 1) TC3_STAMP(2); if (g == 2 * nchunks - 1) TC3_STAMP(3); if (g == 4 * nchunks - 1) TC3_STAMP(4); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -295,6 +333,158 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         const int ups = a.ups;
         const int lq = warp & 3;                     // TMEM lane quarter this warp may access
         const int half = (warp >= 10) ? 1 : 0;       // warps 0-3: columns [0,128), warps 10-13: [128,256)
+        if constexpr (GRP > 1) {
+            // ---- grouped epilogue: lane = (channel cc, tap group g); out[c, t] = sum_g D_g[c, t + g*dil]
+            // Written for instruction count and a small footprint (profiles/r01_tc_grouped_notes.md): one TMEM window per
+            // 16 columns, the per-lane shift folded into the reduce-scatter's selects, residual loads two groups ahead.
+            // (Unrolling the eight groups of a tile to prefetch a whole tile ahead thrashed the instruction cache.)
+                        constexpr int CPW = 32 / GRP, NV = 16 / GRP;
+            const int g = lane & (GRP - 1), cc = lane / GRP;
+            const bool g0 = (g & 1) != 0, g1 = (g & 2) != 0;
+            const int co = lq * CPW + cc;                                   // Rows == 128 / GRP
+            const int coff = (GRP == 4) ? ((g & 1) * 8 + (g >> 1) * 4) : g * 8;   // this lane's columns in a group
+            const int cbeg = half ? 128 : 0;
+            const bool has_res = a.res != nullptr && !(a.dbg & 4);
+            const bool acc_r = a.accum != 0 && !(a.dbg & 4);
+            const bool vec_ok = ((a.y_cs & 3) == 0) && ((a.y_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) &&
+                                (!a.res || (((a.res_cs & 3) == 0) && ((a.res_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0)));
+            const bool relu = a.relu != 0, do_store = !(a.dbg & 8);
+            const float scale = a.scale, post_div = a.post_div;
+            bool fast = false;                                            // interior tile: no bounds checks at all
+            auto prefetch = [&](const float* rr, int q, float* dst) {     // residual values of one column group -> registers
+                if (!has_res) return;
+#pragma unroll
+                for (int j = 0; j < NV / 4; ++j) {
+                    const int qq = q + 4 * j;
+                    if (fast || (vec_ok && qq + 3 < a.Tout)) {
+                        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dst[4 * j]), "=f"(dst[4 * j + 1]), "=f"(dst[4 * j + 2]), "=f"(dst[4 * j + 3]) : "l"(rr + qq));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) asm volatile("ld.global.f32 %0, [%1];" : "=f"(dst[4 * j + e]) : "l"(rr + min(qq + e, a.Tout - 1)));
+                    }
+                }
+            };
+            for (int it = 0; it < my_tiles && ok; ++it) {
+                const int buf = it & 1;
+                int b, rt, q0;
+                decode(it, b, rt, q0);
+                const float* rrow = has_res ? a.res + (long long)b * a.res_bs + (long long)co * a.res_cs : nullptr;
+                const int cend = half ? a.tstep : min(128, a.tstep);
+                fast = vec_ok && (q0 + a.tstep <= a.Tout);
+                float rv[NV], rn[NV];
+                // the first two column groups' residuals are requested before waiting for the accumulator
+                prefetch(rrow, q0 + cbeg + coff, rv);
+                if (cbeg + 16 < cend) prefetch(rrow, q0 + cbeg + 16 + coff, rn);
+                ok = mbar_wait(BAR(ACC_FULL + buf), (it >> 1) & 1, a.err);
+                if (!ok) break;
+                tc_fence_after();
+                if (tid == 0) { if (it == 0) TC3_STAMP(16); if (it == 1) TC3_STAMP(18); if (it == 3) TC3_STAMP(20); }
+                const uint32_t dlane = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16);
+                float bias = a.bias[co];
+                if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + co);
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs;
+#pragma unroll 1
+                for (int cg = cbeg; cg < cend; cg += 16) {
+                    float rf[NV];
+                    if (cg + 32 < cend) prefetch(rrow, q0 + cg + 32 + coff, rf);
+                    {
+                    float S[8], ov[NV];
+                    const int q = q0 + cg + coff;
+                    if (acc_r) {          // accumulate-into-destination (two layers per stage): loaded in place
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) ov[i] = yrow[min(q + i, a.Tout - 1)];
+                    }
+                    if constexpr (DIL > 0) {
+                        // TMEM reads run at ~64 B/clk per SM: one window [cg, cg + 16 + (GRP-1)*DIL) serves all
+                        // groups.  Lane (c, g) needs P[i] = w[i + g*DIL]; the first reduce-scatter step sends
+                        // P[i] or P[i+8] and keeps the other, so the g0 half of the shift is folded into those selects
+                        constexpr int EXT = (GRP - 1) * DIL;
+                        constexpr int EXTN = EXT <= 1 ? 1 : EXT <= 2 ? 2 : EXT <= 4 ? 4 : EXT <= 8 ? 8 : 16;
+                        static_assert(EXT <= 16, "grouped epilogue: shift window too wide");
+                        uint32_t w[16 + EXTN];
+                        tmem_ld_nowait<16>(dlane + (uint32_t)cg, w);
+                        tmem_ld_nowait<EXTN>(dlane + (uint32_t)(cg + 16), w + 16);
+                        tmem_wait_ld();
+                        if constexpr (GRP == 4) {
+#pragma unroll
+                            for (int i = 0; i < 16 + DIL; ++i) w[i] = g1 ? w[i + 2 * DIL] : w[i];   // t[i] = w[i + 2*g1*DIL]
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float send = __uint_as_float(g0 ? w[i + DIL] : w[i + 8]);
+                            const float keep = __uint_as_float(g0 ? w[i + 8 + DIL] : w[i]);
+                            S[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                    } else {
+                        float P[16];
+                        uint32_t l0[16], l1[16];
+                        tmem_ld16_nowait(dlane + (uint32_t)cg, l0);
+                        tmem_ld16_nowait(dlane + (uint32_t)(cg + a.dil), l1);
+                        if constexpr (GRP == 4) {
+                            uint32_t l2[16], l3[16];
+                            tmem_ld16_nowait(dlane + (uint32_t)(cg + 2 * a.dil), l2);
+                            tmem_ld16_nowait(dlane + (uint32_t)(cg + 3 * a.dil), l3);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const uint32_t lo2 = g0 ? l1[i] : l0[i], hi2 = g0 ? l3[i] : l2[i];
+                                P[i] = __uint_as_float(g1 ? hi2 : lo2);
+                            }
+                        } else {
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) P[i] = __uint_as_float(g0 ? l1[i] : l0[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float send = g0 ? P[i] : P[i + 8];
+                            S[i] = (g0 ? P[i + 8] : P[i]) + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                    }
+                    float R[NV];
+                    if constexpr (GRP == 4) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float send = g1 ? S[i] : S[i + 4];
+                            R[i] = (g1 ? S[i + 4] : S[i]) + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) R[i] = S[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        float u = R[i] + bias;
+                        if (relu) u = fmaxf(u, 0.f);
+                        if (has_res) u += rv[i];
+                        u *= scale;
+                        if (acc_r) u += ov[i];
+                        if (post_div != 1.f) u = u / post_div;
+                        R[i] = u;
+                    }
+                    if (do_store) {
+#pragma unroll
+                        for (int j = 0; j < NV / 4; ++j) {
+                            const int qq = q + 4 * j;
+                            if (fast || (vec_ok && qq + 3 < a.Tout)) {
+                                *reinterpret_cast<float4*>(yrow + qq) = make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = R[4 * j + e];
+                            }
+                        }
+                    }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) { rv[i] = rn[i]; rn[i] = rf[i]; }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
+                if (tid == 0) { if (it == 0) TC3_STAMP(17); if (it == 1) TC3_STAMP(19); if (it == 3) TC3_STAMP(21); }
+            }
+            if (tid == 0) TC3_STAMP(22);
+        } else
         for (int it = 0; it < my_tiles && ok; ++it) {
             const int buf = it & 1;
             int b, rt, q0;
@@ -303,109 +493,6 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             if (!ok) break;
             tc_fence_after();
             if (tid == 0) { if (it == 0) TC3_STAMP(16); if (it == 1) TC3_STAMP(18); if (it == 3) TC3_STAMP(20); }
-            if constexpr (GRP > 1) {
-                // ---- grouped epilogue: lane = (channel cc, tap group g); out[c, t] = sum_g D_g[c, t + g*dil]
-                constexpr int CPW = 32 / GRP, NV = 16 / GRP;
-                const int g = lane & (GRP - 1), cc = lane / GRP;
-                const int co = lq * CPW + cc;                                   // Rows == 128 / GRP
-                const uint32_t dlane = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16);
-                const int coff = (GRP == 4) ? ((g & 1) * 8 + (g >> 1) * 4) : g * 8;   // this lane's columns in a chunk
-                const int cbeg = half ? 128 : 0, cend = half ? a.tstep : min(128, a.tstep);
-                float bias = a.bias[co];
-                if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + co);
-                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs;
-                const float* rrow = a.res ? a.res + (long long)b * a.res_bs + (long long)co * a.res_cs : nullptr;
-                const bool acc_r = a.accum != 0 && !(a.dbg & 4);
-                if (a.dbg & 4) rrow = nullptr;
-                const bool vec_ok = ((a.y_cs & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
-                                    ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
-                                    (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-                float rv[NV], ov[NV];
-                auto prefetch = [&](int cg, float* r_, float* o_) {
-                    const int q = q0 + cg + coff;
-#pragma unroll
-                    for (int j = 0; j < NV / 4; ++j) {
-                        const int qq = q + 4 * j;
-                        if (vec_ok && qq + 3 < a.Tout) {
-                            if (rrow) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rrow + qq));
-                            if (acc_r) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int qe = min(qq + e, a.Tout - 1);
-                                if (rrow) asm volatile("ld.global.f32 %0, [%1];" : "=f"(r_[4 * j + e]) : "l"(rrow + qe));
-                                if (acc_r) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
-                            }
-                        }
-                    }
-                };
-                prefetch(cbeg, rv, ov);
-                for (int cg = cbeg; cg < cend; cg += 16) {
-                    float rn[NV], on[NV], P[16];
-                    if (cg + 16 < cend) prefetch(cg + 16, rn, on);
-                    {
-                        float l0[16], l1[16];
-                        tmem_ld16(dlane + (uint32_t)cg, l0);
-                        tmem_ld16(dlane + (uint32_t)(cg + a.dil), l1);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) P[i] = (g & 1) ? l1[i] : l0[i];
-                    }
-                    if constexpr (GRP == 4) {
-                        float l2[16], l3[16];
-                        tmem_ld16(dlane + (uint32_t)(cg + 2 * a.dil), l2);
-                        tmem_ld16(dlane + (uint32_t)(cg + 3 * a.dil), l3);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { const float hi2 = (g & 1) ? l3[i] : l2[i]; P[i] = (g & 2) ? hi2 : P[i]; }
-                    }
-                    // shuffle reduce-scatter over the GRP adjacent lanes of a channel
-                    float S[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float send = (g & 1) ? P[i] : P[i + 8];
-                        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                        S[i] = ((g & 1) ? P[i + 8] : P[i]) + recv;
-                    }
-                    float R[NV];
-                    if constexpr (GRP == 4) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float send = (g & 2) ? S[i] : S[i + 4];
-                            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-                            R[i] = ((g & 2) ? S[i + 4] : S[i]) + recv;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) R[i] = S[i];
-                    }
-                    const int q = q0 + cg + coff;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        float u = R[i] + bias;
-                        if (a.relu) u = fmaxf(u, 0.f);
-                        if (rrow) u += rv[i];
-                        u *= a.scale;
-                        if (acc_r) u += ov[i];
-                        if (a.post_div != 1.f) u = u / a.post_div;
-                        R[i] = u;
-                    }
-                    if (!(a.dbg & 8))
-#pragma unroll
-                    for (int j = 0; j < NV / 4; ++j) {
-                        const int qq = q + 4 * j;
-                        if (vec_ok && qq + 3 < a.Tout) {
-                            *reinterpret_cast<float4*>(yrow + qq) = make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = R[4 * j + e];
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) { rv[i] = rn[i]; ov[i] = on[i]; }
-                }
-                tc_fence_before();
-                mbar_arrive(BAR(ACC_EMPTY + buf));
-                continue;
-            }
             const int r = rt * MROWS + lq * 32 + lane;             // GEMM row of this lane
             const bool rok = r < a.Rows;
             const int rc = rok ? r : a.Rows - 1;
@@ -475,10 +562,11 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         }
                     }
                 };
-                if (rok) prefetch(0, rv, ov);
+                const bool ld_ok = rok && !(a.dbg & 4), st_ok = rok && !(a.dbg & 8);
+                if (ld_ok) prefetch(0, rv, ov);
                 for (int cg = 0; cg < 128; cg += 16) {
                     float v[16], rn[16], on[16];
-                    if (rok && cg + 16 < 128) prefetch(cg + 16, rn, on);
+                    if (ld_ok && cg + 16 < 128) prefetch(cg + 16, rn, on);
                     tmem_ld16(dbase + (uint32_t)cg, v);
                     const int q = qb + cg;
 #pragma unroll
@@ -494,7 +582,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         if (mpost_r) u *= mk;
                         v[i] = u;
                     }
-                    if (rok) {
+                    if (st_ok) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int qq = q + 4 * j;
@@ -529,7 +617,8 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 }
             }
             tc_fence_before();
-            mbar_arrive(BAR(ACC_EMPTY + buf));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));   // one arrival per epilogue warp
             if (tid == 0) { if (it == 0) TC3_STAMP(17); if (it == 1) TC3_STAMP(19); if (it == 3) TC3_STAMP(21); }
         }
         if (tid == 0) TC3_STAMP(22);
@@ -542,9 +631,16 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) { tc3_body<1>(a); }
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g2_kernel(const Tc3Args a) { tc3_body<2>(a); }
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g4_kernel(const Tc3Args a) { tc3_body<4>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) { tc3_body<1, 0>(a); }
+template <int GRP, int DIL>
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g_kernel(const Tc3Args a) { tc3_body<GRP, DIL>(a); }
+
+typedef void (*Tc3Kernel)(const Tc3Args);
+// grouped kernel for (tap groups, dilation): dilations 1 / 3 / 5 (the HiFiGAN resblocks) are specialised
+static inline Tc3Kernel grouped_kernel(int grp, int dil) {
+    if (grp == 2) return dil == 1 ? conv1d_tc3g_kernel<2, 1> : dil == 3 ? conv1d_tc3g_kernel<2, 3> : dil == 5 ? conv1d_tc3g_kernel<2, 5> : conv1d_tc3g_kernel<2, 0>;
+    return dil == 1 ? conv1d_tc3g_kernel<4, 1> : dil == 3 ? conv1d_tc3g_kernel<4, 3> : dil == 5 ? conv1d_tc3g_kernel<4, 5> : conv1d_tc3g_kernel<4, 0>;
+}
 
 }  // namespace tc3
 }  // namespace b200tts
