@@ -85,17 +85,26 @@ struct ConvKArgs {
 
 enum : int { KEPI_GENERIC = 0, KEPI_GATE = 1, KEPI_TANH = 2, KEPI_PLAIN = 3 };
 
-// CJ rows x TJ time steps per lane, WCO x WT warps, CIC input channels per stage, EPI epilogue family
-template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI>
-__global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d_kernel(const ConvKArgs a) {
+// CJ rows x TJ time steps per lane, WCO x WT warps, CIC input channels per stage, EPI epilogue family.
+// KG > 1: intra-CTA split-K for launch-starved shapes (text encoder / duration predictor: 64 frames x 32 utterances
+// give only 96 CTAs of 4 warps) -- KG warp groups each own a double-buffered stage and every KG-th channel chunk of
+// the SAME output tile; their accumulators are summed through shared memory in a fixed order (deterministic).
+template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI, int KG = 1>
+__global__ void __launch_bounds__(32 * WCO * WT * KG, (KG > 1) ? 1 : ((WCO * WT >= 8) ? 2 : 3)) conv1d_kernel(const ConvKArgs a) {
     constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT;
     extern __shared__ __align__(16) float smem[];
     const int XS = a.XS;
     const int wchunk = CIC * a.K * CO_T;
-    float* xs0 = smem;
-    float* ws0 = smem + 2 * CIC * XS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kg = (KG > 1) ? (int)(threadIdx.x / NT) : 0;              // split-K group of this warp
+    const int stage_floats = 2 * CIC * XS + 2 * wchunk;
+    float* xs0 = smem + (size_t)kg * stage_floats;
+    float* ws0 = xs0 + 2 * CIC * XS;
+    const int tid = threadIdx.x % NT, lane = tid & 31, warp = tid >> 5;   // group-local thread / warp index
     const int wco = warp % WCO, wt = warp / WCO;
+    auto group_sync = [&]() {
+        if constexpr (KG > 1) asm volatile("bar.sync %0, %1;" ::"r"(kg + 1), "r"(NT) : "memory");
+        else __syncthreads();
+    };
     const int b = blockIdx.z, tile_co = blockIdx.y;
     const int q0 = blockIdx.x * T_T;
     const int tin0 = q0 - a.pad;
@@ -141,14 +150,14 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
 #pragma unroll
         for (int j = 0; j < TJ; ++j) acc[p][j] = 0ull;
 
-    load_chunk(0, 0);
+    if (kg < nchunks) load_chunk(kg, 0);
     cp_async_wait_all();
-    __syncthreads();
+    group_sync();
 
     const int K = a.K, dil = a.dil;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = ch & 1;
-        if (ch + 1 < nchunks) load_chunk(ch + 1, buf ^ 1);
+    for (int ch = kg, it = 0; ch < nchunks; ch += KG, ++it) {
+        const int buf = it & 1;
+        if (ch + KG < nchunks) load_chunk(ch + KG, buf ^ 1);
         const float* xr = xs0 + buf * CIC * XS + wt * 32 * TJ + lane;
         const float* wr = ws0 + buf * wchunk + wco * CJ;
 #pragma unroll 1
@@ -176,7 +185,32 @@ __global__ void __launch_bounds__(32 * WCO * WT, (WCO * WT >= 8) ? 2 : 3) conv1d
             }
         }
         cp_async_wait_all();
+        group_sync();
+    }
+
+    if constexpr (KG > 1) {
+        // fixed-order sum of the groups' partial accumulators (group 0 += group 1 += ...), through the stage memory
         __syncthreads();
+        u64* red = reinterpret_cast<u64*>(smem);
+        if (kg > 0) {
+#pragma unroll
+            for (int p = 0; p < CJ / 2; ++p)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) red[(((size_t)(kg - 1) * (CJ / 2) + p) * TJ + j) * NT + tid] = acc[p][j];
+        }
+        __syncthreads();
+        if (kg > 0) return;
+#pragma unroll
+        for (int g2 = 1; g2 < KG; ++g2)
+#pragma unroll
+            for (int p = 0; p < CJ / 2; ++p)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) {
+                    float v0, v1, w0, w1;
+                    unpack2(acc[p][j], v0, v1);
+                    unpack2(red[(((size_t)(g2 - 1) * (CJ / 2) + p) * TJ + j) * NT + tid], w0, w1);
+                    acc[p][j] = pack2(v0 + w0, v1 + w1);
+                }
     }
 
     // ---------------------------------------------------------------- epilogue
@@ -566,22 +600,23 @@ __global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ host: launch
-template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI>
+template <int CJ, int TJ, int WCO, int WT, int CIC, int EPI, int KG = 1>
 static int launch_variant(const ConvKArgs& ka, int B, int RowsPad, cudaStream_t st) {
-    constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT;
+    constexpr int CO_T = CJ * WCO, T_T = 32 * TJ * WT, NT = 32 * WCO * WT * KG;
     ConvKArgs a = ka;
     a.XS = round_up(T_T + (a.K - 1) * a.dil, 4);
-    const size_t smem = (size_t)(2 * CIC * a.XS + 2 * CIC * a.K * CO_T) * sizeof(float);
+    size_t smem = (size_t)KG * (2 * CIC * a.XS + 2 * CIC * a.K * CO_T) * sizeof(float);
+    if (KG > 1) smem = std::max(smem, (size_t)(KG - 1) * (CJ / 2) * TJ * (NT / KG) * sizeof(u64));
     B200_REQUIRE(smem <= 227 * 1024, "conv1d: K=%d dil=%d needs %zu B of shared memory", a.K, a.dil, smem);
     static bool attr_done = false;
     if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI>,
+        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI, KG>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     dim3 grid((a.Tq + T_T - 1) / T_T, RowsPad / CO_T, B);
     B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv1d: grid too large");
-    conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI><<<grid, NT, smem, st>>>(a);
+    conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI, KG><<<grid, NT, smem, st>>>(a);
     count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -591,6 +626,16 @@ template <int CIC, int EPI>
 static int launch_tiles(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaStream_t st) {
     const bool small_t = a.Tq <= 128;
     if (co_tile == 64) {
+        if constexpr (EPI == KEPI_PLAIN) {
+            // launch-starved shape (fewer CTAs than SMs, long channel loop): split the channel chunks over 4 warp groups
+            static int splitk = -1;
+            if (splitk < 0) { const char* e = getenv("B200TTS_NO_SPLITK"); splitk = (e && atoi(e)) ? 0 : 1; }
+            const long long ctas = (long long)((a.Tq + 63) / 64) * (RowsPad / 64) * B;
+            const int nchunks = (a.Cin + CIC - 1) / CIC;
+            const size_t smem4 = (size_t)4 * (2 * CIC * round_up(64 + (a.K - 1) * a.dil, 4) + 2 * CIC * a.K * 64) * sizeof(float);
+            if (splitk && small_t && ctas <= 160 && nchunks >= 8 && smem4 <= 200 * 1024)
+                return launch_variant<16, 2, 4, 1, CIC, EPI, 4>(a, B, RowsPad, st);
+        }
         if (small_t) return launch_variant<16, 2, 4, 1, CIC, EPI>(a, B, RowsPad, st);
         return launch_variant<16, 4, 4, 2, CIC, EPI>(a, B, RowsPad, st);
     }
