@@ -26,9 +26,15 @@ __device__ __forceinline__ void column_stats(float partial_sum, float (*red)[33]
 }
 
 // y = GELU(LN(depthwise_conv_k(x * mask)))          (DDSConv first half, sdp.py:55-57)
-__global__ void __launch_bounds__(256) dds_sep_ln_gelu_kernel(const float* x, const float* mask, const float* w,
-                                                             const float* bias, const float* gamma, const float* beta,
-                                                             float* y, int C, int T, int K, int dil) {
+// Each thread owns one time step and every 8th channel; its <= DDS_MAXC values stay in registers between the conv,
+// the two LayerNorm reductions and the store (all global loads of a pass are issued before the first use: with 64
+// CTAs per launch this kernel is pure load latency).
+constexpr int DDS_MAXC = 32;   // channels per thread (C <= 256)
+
+__global__ void __launch_bounds__(256) dds_sep_ln_gelu_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ y, int C, int T, int K, int dil) {
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + tx, b = blockIdx.y;
@@ -36,53 +42,74 @@ __global__ void __launch_bounds__(256) dds_sep_ln_gelu_kernel(const float* x, co
     const size_t base = (size_t)b * C * T;
     const float* mb = mask + (size_t)b * T;
     const int pad = (K * dil - dil) / 2;
-    float s = 0.f;
-    if (ok)
-        for (int c = ty; c < C; c += 8) {
-            float a = bias[c];
-            for (int k = 0; k < K; ++k) {
-                const int ti = t + k * dil - pad;
-                if (ti >= 0 && ti < T) a = fmaf(w[c * K + k], x[base + (size_t)c * T + ti] * mb[ti], a);
-            }
-            y[base + (size_t)c * T + t] = a;
-            s += a;
+    float av[DDS_MAXC];
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) av[u] = 0.f;
+    if (ok) {
+#pragma unroll
+        for (int u = 0; u < DDS_MAXC; ++u) { const int c = ty + 8 * u; if (c < C) av[u] = bias[c]; }
+        for (int k = 0; k < K; ++k) {            // same accumulation order as before: taps outer-to-inner per channel
+            const int ti = t + k * dil - pad;
+            if (ti < 0 || ti >= T) continue;
+            const float mk = mb[ti];
+            float xv[DDS_MAXC];
+#pragma unroll
+            for (int u = 0; u < DDS_MAXC; ++u) { const int c = ty + 8 * u; xv[u] = (c < C) ? x[base + (size_t)c * T + ti] : 0.f; }
+#pragma unroll
+            for (int u = 0; u < DDS_MAXC; ++u) { const int c = ty + 8 * u; if (c < C) av[u] = fmaf(w[c * K + k], xv[u] * mk, av[u]); }
         }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) if (ty + 8 * u < C) s += av[u];
     float mean, var;
     column_stats(s, red, tx, ty, C, mean);
     float v = 0.f;
-    if (ok)
-        for (int c = ty; c < C; c += 8) { const float d = y[base + (size_t)c * T + t] - mean; v += d * d; }
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) if (ty + 8 * u < C) { const float d = av[u] - mean; v += d * d; }
     column_stats(v, red, tx, ty, C, var);
     if (!ok) return;
     const float rstd = rsqrtf(var + 1e-5f);
-    for (int c = ty; c < C; c += 8) {
-        const size_t i = base + (size_t)c * T + t;
-        y[i] = gelu_erf((y[i] - mean) * rstd * gamma[c] + beta[c]);
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) {
+        const int c = ty + 8 * u;
+        if (c < C) y[base + (size_t)c * T + t] = gelu_erf((av[u] - mean) * rstd * gamma[c] + beta[c]);
     }
 }
 
 // x = x + GELU(LN(y))  (* mask after the last layer)        (DDSConv second half, sdp.py:59-63)
-__global__ void __launch_bounds__(256) dds_ln_gelu_res_kernel(float* x, const float* y, const float* gamma,
-                                                             const float* beta, const float* mask, int C, int T,
-                                                             int apply_mask) {
+__global__ void __launch_bounds__(256) dds_ln_gelu_res_kernel(float* __restrict__ x, const float* __restrict__ y,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ mask, int C, int T, int apply_mask) {
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + tx, b = blockIdx.y;
     const bool ok = t < T;
     const size_t base = (size_t)b * C * T + t;
+    float yv[DDS_MAXC], xv[DDS_MAXC];
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) {
+        const int c = ty + 8 * u;
+        const bool in = ok && c < C;
+        yv[u] = in ? y[base + (size_t)c * T] : 0.f;
+        xv[u] = in ? x[base + (size_t)c * T] : 0.f;
+    }
     float s = 0.f;
-    if (ok) for (int c = ty; c < C; c += 8) s += y[base + (size_t)c * T];
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) if (ty + 8 * u < C) s += yv[u];
     float mean, var;
     column_stats(s, red, tx, ty, C, mean);
     float v = 0.f;
-    if (ok) for (int c = ty; c < C; c += 8) { const float d = y[base + (size_t)c * T] - mean; v += d * d; }
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) if (ty + 8 * u < C) { const float d = yv[u] - mean; v += d * d; }
     column_stats(v, red, tx, ty, C, var);
     if (!ok) return;
     const float rstd = rsqrtf(var + 1e-5f);
     const float m = apply_mask ? mask[(size_t)b * T + t] : 1.f;
-    for (int c = ty; c < C; c += 8) {
-        const size_t i = base + (size_t)c * T;
-        x[i] = (x[i] + gelu_erf((y[i] - mean) * rstd * gamma[c] + beta[c])) * m;
+#pragma unroll
+    for (int u = 0; u < DDS_MAXC; ++u) {
+        const int c = ty + 8 * u;
+        if (c < C) x[base + (size_t)c * T] = (xv[u] + gelu_erf((yv[u] - mean) * rstd * gamma[c] + beta[c])) * m;
     }
 }
 
@@ -316,6 +343,7 @@ int DDSConv::init(int channels, int kernel_size, int num_layers, const float* co
 
 // x [B,C,T] updated in place; y1,y2 scratch [B,C,T]
 int DDSConv::forward(float* x, const float* mask, int B, int T, float* y1, float* y2, cudaStream_t st) const {
+    B200_REQUIRE(C <= 8 * DDS_MAXC, "DDSConv: %d channels exceed the kernel's register column (%d)", C, 8 * DDS_MAXC);
     dim3 grid((T + 31) / 32, B);
     int dil = 1, rc;
     for (int l = 0; l < L; ++l) {

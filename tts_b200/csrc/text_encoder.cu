@@ -31,9 +31,9 @@ constexpr int ATT_KT = 32;      // keys per tile
 constexpr int ATT_MAXD = 256;   // max head dim (8 values per lane)
 
 // qkv [B, 3C, T] (q rows 0..C, k rows C..2C, v rows 2C..3C), head h owns channels [h*d, (h+1)*d)
-__global__ void __launch_bounds__(32 * ATT_Q) rel_attention_kernel(const float* qkv, const float* mask,
-                                                                  const float* emb_rel_k, const float* emb_rel_v,
-                                                                  float* out, int C, int T, int d, int window,
+__global__ void __launch_bounds__(32 * ATT_Q) rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ mask,
+                                                                  const float* __restrict__ emb_rel_k, const float* __restrict__ emb_rel_v,
+                                                                  float* __restrict__ out, int C, int T, int d, int window,
                                                                   float inv_sqrt_d) {
     extern __shared__ float sm[];
     const int Tp = (T + 31) & ~31;
@@ -60,9 +60,22 @@ __global__ void __launch_bounds__(32 * ATT_Q) rel_attention_kernel(const float* 
     // ---- scores = q.k / sqrt(d)
     for (int j0 = 0; j0 < T; j0 += ATT_KT) {
         __syncthreads();
-        for (int idx = tid; idx < d * ATT_KT; idx += blockDim.x) {
-            const int c = idx / ATT_KT, jj = idx - c * ATT_KT, j = j0 + jj;
-            kt[c * (ATT_KT + 1) + jj] = (j < T) ? kb[(size_t)c * T + j] : 0.f;
+        // all global loads of a batch are issued before the first shared store (in-order issue would otherwise
+        // expose one full memory latency per element: profiles/r01_tc_notes.md, finding 1)
+        for (int i0b = 0; i0b < d * ATT_KT; i0b += 8 * 32 * ATT_Q) {
+            float tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0b + u * 32 * ATT_Q + tid;
+                const int c = idx / ATT_KT, jj = idx - c * ATT_KT, j = j0 + jj;
+                tmp[u] = (idx < d * ATT_KT && j < T) ? kb[(size_t)c * T + j] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0b + u * 32 * ATT_Q + tid;
+                const int c = idx / ATT_KT, jj = idx - c * ATT_KT;
+                if (idx < d * ATT_KT) kt[c * (ATT_KT + 1) + jj] = tmp[u];
+            }
         }
         __syncthreads();
         if (active) {
@@ -116,9 +129,20 @@ __global__ void __launch_bounds__(32 * ATT_Q) rel_attention_kernel(const float* 
     float* vt = kt;  // [ATT_KT][d+1]
     for (int j0 = 0; j0 < T; j0 += ATT_KT) {
         __syncthreads();
-        for (int idx = tid; idx < d * ATT_KT; idx += blockDim.x) {
-            const int c = idx / ATT_KT, jj = idx - c * ATT_KT, j = j0 + jj;
-            vt[jj * (d + 1) + c] = (j < T) ? vb[(size_t)c * T + j] : 0.f;
+        for (int i0b = 0; i0b < d * ATT_KT; i0b += 8 * 32 * ATT_Q) {
+            float tmp[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0b + u * 32 * ATT_Q + tid;
+                const int c = idx / ATT_KT, jj = idx - c * ATT_KT, j = j0 + jj;
+                tmp[u] = (idx < d * ATT_KT && j < T) ? vb[(size_t)c * T + j] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = i0b + u * 32 * ATT_Q + tid;
+                const int c = idx / ATT_KT, jj = idx - c * ATT_KT;
+                if (idx < d * ATT_KT) vt[jj * (d + 1) + c] = tmp[u];
+            }
         }
         __syncthreads();
         if (active) {
