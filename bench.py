@@ -29,8 +29,8 @@ HIFIGAN_FLOP_PER_SAMPLE = 2.402e6      # SURVEY.md section 8d (Cin=192)
 FLOW_FLOP_PER_FRAME = 14.16e6
 FP32_FMA_PEAK_TFLOPS = 73.5            # measured on this pool with tools/microbench_fma.cu (FFMA2), see DESIGN.md
 # dram__bytes_read+write summed over the 78 conv launches of one HiFiGAN pass at this workload's shape (B=32, 192
-# padded frames), from one ncu capture: profiles/r01_decoder_dram_traffic.csv (19.8 GB read + 8.9 GB written)
-DECODER_DRAM_BYTES_PER_PASS = {6144: 28.72e9}
+# padded frames), from one ncu capture: profiles/r01_decoder_dram_traffic_final.csv (19.79 GB read + 8.89 GB written)
+DECODER_DRAM_BYTES_PER_PASS = {6144: 28.68e9}
 
 
 def load_peaks():
@@ -327,15 +327,15 @@ def run_cuda(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv1d_tc_kernel + conv1d_kernel (all HiFiGAN launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "conv1d_tc3_kernel + conv1d_tc3g_kernel<GRP,DIL> + conv1d_row1_kernel (the 78 HiFiGAN launches of a step; conv1d_tc3_kernel alone is 56 % of the step)",
                          "achieved": dec_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (dec_tflops / peaks["bf16_tflops_sustained"]) if dec_tflops else None,
                          "traffic": DECODER_DRAM_BYTES_PER_PASS.get(frames_padded // args.steps),
                          "traffic_unit": "bytes per decoder pass (78 launches), ncu dram__bytes_read+write; algorithmic layer-granular = 21.2 KB/sample",
                          "peak_source": peaks["source"],
                          "note": "algorithmic fp32 FLOPs; the MRF/pre convs run on tcgen05 kind::tf32 as 3xTF32 (3 MMAs per "
-                                 "algorithmic MAC at half the bf16 rate => ceiling = peak/6), upsamplers/post on the FP32 "
-                                 f"FMA pipe (measured peak {FP32_FMA_PEAK_TFLOPS} TFLOP/s)",
+                                 "algorithmic MAC at half the bf16 rate => ceiling = peak/6); conv_post is a streaming FP32 kernel "
+                                 f"(FP32 FMA peak measured {FP32_FMA_PEAK_TFLOPS} TFLOP/s)",
                          "frac_of_3xtf32_ceiling": (dec_tflops / (peaks["bf16_tflops_sustained"] / 6.0)) if dec_tflops else None,
                          "frac_fp32_fma": (dec_tflops / FP32_FMA_PEAK_TFLOPS) if dec_tflops else None},
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
