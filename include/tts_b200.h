@@ -115,6 +115,12 @@ size_t b200tts_flow_workspace_bytes(const b200tts_flow* h, int B, int T);
 int b200tts_flow_reverse(const b200tts_flow* h, float* z, const float* mask, const float* g, int B, int T,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- latent upsampling (VitsArgs.encoder_sample_rate) -----------------------------------------
+ * Replaces torch.nn.functional.interpolate(z, scale_factor=[f], mode="linear") in Vits.upsampling_z,
+ * TTS/tts/models/vits.py:944-959.  x [rows, Tin] -> y [rows, Tout], Tout = floor(Tin * f) chosen by the caller.
+ */
+int b200tts_upsample_linear(const float* x, int rows, int Tin, float scale_factor, float* y, int Tout, void* stream);
+
 /* ---- posterior encoder (training / voice conversion) ----------------------------------------
  * Replaces PosteriorEncoder.forward, TTS/tts/layers/vits/networks.py:275-288.
  * weights: pre.w [H,Cin,1], pre.b, [enc.cond_layer.w, .b], per WN layer enc.in_layers[i].w,.b, enc.res_skip_layers[i].w,.b,

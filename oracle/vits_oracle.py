@@ -170,7 +170,7 @@ def posterior_encoder(sd, y, y_lengths, g=None, noise=None, *, out_channels=192,
 def sequence_mask(lengths, max_len=None):
     """tts/utils/helpers.py:43-57."""
     if max_len is None:
-        max_len = int(lengths.max())
+        max_len = lengths.max()          # a 0-dim tensor, like the reference: float lengths give ceil(max) columns
     return torch.arange(max_len, dtype=lengths.dtype, device=lengths.device)[None, :] < lengths[:, None]
 
 
@@ -418,6 +418,10 @@ def vits_inference(sd, tokens, x_lengths, sdp_noise, prior_noise_fn, *, args, sp
     z = flow_forward(sub(sd, "flow"), z_p, y_mask, g=g, reverse=True, hidden=hid,
                      kernel_size=a["kernel_size_flow"], dilation_rate=a["dilation_rate_flow"],
                      num_layers=a["num_layers_flow"])
+    if a.get("encoder_sample_rate") and a.get("interpolate_z", True):   # upsampling_z, vits.py:944-959
+        f = a["sample_rate"] / a["encoder_sample_rate"]
+        z = F.interpolate(z, scale_factor=[f], mode="linear").squeeze(0)
+        y_mask = sequence_mask(y_lengths * f, None).to(y_mask.dtype).unsqueeze(1)
     mil = a.get("max_inference_len", None)
     o = hifigan_forward(sub(sd, "waveform_decoder"), (z * y_mask)[:, :, :mil], g=g,
                         upsample_factors=a["upsample_rates_decoder"],

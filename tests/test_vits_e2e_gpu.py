@@ -170,3 +170,51 @@ def test_voice_conversion(mode):
     o3, _, _ = m.voice_conversion(y_dev, torch.tensor([y.shape[-1]] * 2).cuda(), src.cuda(), tgt.cuda(),
                                   posterior_noise=noise.cuda())
     assert torch.equal(o2, o3) and torch.isfinite(o2).all() and o2.shape == (2, 1, y.shape[-1] * 256)
+
+
+def test_encoder_sample_rate_upsampling():
+    """VitsArgs.encoder_sample_rate: z is linearly interpolated by sample_rate / encoder_sample_rate before the
+    decoder and the mask is rebuilt (Vits.upsampling_z, vits.py:944-959)."""
+    from tts_b200.vits import Vits, VitsArgs, VitsAudioConfig, VitsConfig
+    args = VitsArgs(encoder_sample_rate=11025, upsample_rates_decoder=[8, 8, 4, 2],
+                    upsample_kernel_sizes_decoder=[16, 16, 8, 4])
+    cfg = VitsConfig(model_args=args, audio=VitsAudioConfig(sample_rate=22050))
+    assert Vits.init_from_config(cfg) is not None          # 8*8*4*2 == 256 * 2 (vits.py:1789-1794)
+    with pytest.raises(AssertionError):
+        Vits.init_from_config(VitsConfig(model_args=VitsArgs(encoder_sample_rate=11025)))
+    torch.manual_seed(21)
+    m = Vits(cfg).eval()
+    _perturb(m, 21)
+    a = _args_dict(args)
+    a["sample_rate"] = 22050
+    b, t = 3, 18
+    tok, lens = torch.randint(0, 100, (b, t)), torch.tensor([18, 9, 3])
+    sdp_noise = torch.randn(b, 2, t)
+    store = {}
+
+    def prior_noise(shape):
+        store["n"] = torch.randn(shape, generator=torch.Generator().manual_seed(5))
+        return store["n"]
+
+    want = O.vits_inference(m.state_dict(), tok, lens, sdp_noise, prior_noise, args=a)
+    m.cuda()
+    got = m.inference(tok.cuda(), {"x_lengths": lens.cuda()}, sdp_noise=sdp_noise,
+                      prior_noise=lambda s: store["n"].cuda())
+    assert got["z"].shape == want["z"].shape and got["z"].shape[-1] == 2 * got["z_p"].shape[-1]
+    assert torch.equal(got["y_mask"].cpu(), want["y_mask"])
+    assert (got["z"].cpu() - want["z"]).abs().max() < 2e-4
+    assert got["model_outputs"].shape == want["model_outputs"].shape == (b, 1, got["z"].shape[-1] * 512)
+    rms = (got["model_outputs"].cpu() - want["model_outputs"]).pow(2).mean().sqrt().item()
+    assert rms <= 1e-4, rms
+
+
+def test_upsample_linear_matches_torch():
+    import torch.nn.functional as F
+    from tts_b200.layers import upsample_linear
+    torch.manual_seed(3)
+    for f in (2.0, 1.5, 22050 / 16000):
+        z = torch.randn(2, 7, 40)
+        want = F.interpolate(z, scale_factor=[f], mode="linear")
+        got = upsample_linear(z.cuda(), f).cpu()
+        assert got.shape == want.shape
+        assert (got - want).abs().max() < 1e-6, f

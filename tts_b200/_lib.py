@@ -103,6 +103,8 @@ def _declare(lib):
     lib.b200tts_posterior_forward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, sz, vp]
     lib.b200tts_duration_predictor_forward.restype = ci
     lib.b200tts_duration_predictor_forward.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, vp, sz, vp]
+    lib.b200tts_upsample_linear.restype = ci
+    lib.b200tts_upsample_linear.argtypes = [vp, ci, ci, cf, vp, ci, vp]
     lib.b200tts_flow_reverse.restype = ci
     lib.b200tts_flow_reverse.argtypes = [vp, vp, vp, vp, ci, ci, vp, sz, vp]
     lib.b200tts_text_encoder_forward.restype = ci

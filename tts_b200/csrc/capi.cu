@@ -137,6 +137,10 @@ int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y
                                m_p, logs_p, z_p, y_mask, (cudaStream_t)stream);
 }
 
+int b200tts_upsample_linear(const float* x, int rows, int Tin, float scale_factor, float* y, int Tout, void* stream) {
+    return launch_upsample_linear(x, rows, Tin, scale_factor, y, Tout, (cudaStream_t)stream);
+}
+
 int b200tts_stft_create(int n_fft, int hop_length, const float* window, const float* mel_basis, int n_mels,
                         b200tts_stft** out) {
     if (!out) { set_error("stft_create: null argument"); return 1; }

@@ -69,6 +69,7 @@ struct DurPred {
                 void* ws, size_t ws_bytes, cudaStream_t st) const;
 };
 
+int launch_upsample_linear(const float* x, int rows, int Tin, float scale_factor, float* y, int Tout, cudaStream_t st);
 int launch_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, const float* mask,
                          float* out, int B, int C, int T, float eps, cudaStream_t st);
 

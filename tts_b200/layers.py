@@ -614,3 +614,17 @@ def expand_prior(cum, x_mask, y_lengths, stats, noise, noise_scale, t_dec, want_
                                              _lib.ptr(y_mask), _lib.stream_ptr(dev))
     _lib.check(rc, "expand_prior")
     return attn, m_p, logs_p, z_p, y_mask
+
+
+def upsample_linear(z, scale_factor):
+    """F.interpolate(z, scale_factor=[f], mode="linear") on the device (vits.py:952): [B,C,T] -> [B,C,floor(T*f)]."""
+    _lib.require_cuda(z, "z")
+    z = z.to(torch.float32).contiguous()
+    b, c, t = z.shape
+    t_out = int(math.floor(t * float(scale_factor)))
+    out = torch.empty((b, c, t_out), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        rc = _lib.lib().b200tts_upsample_linear(_lib.ptr(z), b * c, t, ctypes.c_float(scale_factor), _lib.ptr(out), t_out,
+                                                _lib.stream_ptr(z.device))
+    _lib.check(rc, "upsample_linear")
+    return out

@@ -17,6 +17,7 @@ from torch import nn
 
 from . import _lib
 from .hifigan import HifiganGenerator
+from .layers import upsample_linear
 from .layers import (DurationPredictor, EngineModule, PosteriorEncoder, ResidualCouplingBlocks, StochasticDurationPredictor,
                      TextEncoder, durations_to_path, expand_prior)
 
@@ -178,8 +179,8 @@ class Vits(nn.Module):
         self.noise_scale_dp = a.noise_scale_dp
         self.max_inference_len = a.max_inference_len
         self.spec_segment_size = a.spec_segment_size
-        if a.encoder_sample_rate:
-            raise NotImplementedError("tts_b200: encoder_sample_rate (z interpolation, vits.py:944-959) is not built")
+        if a.encoder_sample_rate:   # vits.py:809-810 (the training-only torchaudio resampler is not needed here)
+            self.interpolate_factor = _get(config, "audio")["sample_rate"] / a.encoder_sample_rate
 
         self.text_encoder = TextEncoder(a.num_chars, a.hidden_channels, a.hidden_channels,
                                         a.hidden_channels_ffn_text_encoder, a.num_heads_text_encoder,
@@ -244,8 +245,11 @@ class Vits(nn.Module):
         up = 1
         for u in _get(config, "model_args").upsample_rates_decoder:
             up *= u
-        assert up == _get(config, "audio").hop_length, (
-            f" [!] Product of upsample rates must be equal to the hop length - {up} vs {_get(config, 'audio').hop_length}")
+        hop = _get(config, "audio").hop_length
+        esr = _get(config, "model_args").encoder_sample_rate
+        if esr:   # vits.py:1789-1794
+            hop = hop * (_get(config, "audio").sample_rate / esr)
+        assert up == hop, f" [!] Product of upsample rates must be equal to the hop length - {up} vs {hop}"
         return Vits(config)
 
     # ------------------------------------------------------------------ conditioning (vits.py:874-905)
@@ -336,6 +340,14 @@ class Vits(nn.Module):
                                                           want_attn=return_alignments)
         with _Stage(self, "flow"):
             z = self.flow(z_p, y_mask, g=g, reverse=True)
+            if a.encoder_sample_rate and a.interpolate_z:   # upsampling_z, vits.py:944-959
+                f = self.interpolate_factor
+                z = upsample_linear(z, f)
+                len_up = y_lengths * f
+                y_mask = (torch.arange(float(len_up.max()), device=z.device)[None, :] < len_up[:, None]).to(y_mask.dtype).unsqueeze(1)
+                if y_mask.shape[-1] != z.shape[-1]:
+                    raise ValueError("tts_b200.Vits: sample_rate / encoder_sample_rate must scale the frame count to an "
+                                     "integer (the reference's z * y_mask fails the same way, vits.py:1160)")
             zin = z * y_mask
             if self.max_inference_len is not None:
                 zin = zin[:, :, : self.max_inference_len]
