@@ -137,12 +137,15 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
             a3.n_ttiles = (T + a3.tstep - 1) / a3.tstep; a3.n_rtiles = 1;
         }
         smem2 = smem_bytes3(a3.rows_pad, a3.raw_w);
+        const bool staged = getenv("TC_STAGE") && G == 1;
+        if (staged) { a3.stage = 1; a3.stage_off = (int)((smem2 + 15) / 16 * 16); smem2 = (size_t)a3.stage_off + STAGE_BYTES; CK(cudaFuncSetAttribute(conv1d_tc3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
         if (G > 1) CK(cudaFuncSetAttribute(grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         const int tiles = a3.B * a3.n_ttiles * a3.n_rtiles;
         grid2 = dim3(tiles < sms ? tiles : sms);
         if (G > 1) grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        else if (staged) conv1d_tc3s_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         else conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
     } else if (v2) {
         using namespace b200tts::tc2;
@@ -175,6 +178,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
         sumsq += d * d;
     }
     if (G > 1) printf("grouped G=%d ", G);
+    if (a3.stage) printf("staged ");
     printf("%s smem=%zu err_flag=%d max_err=%.3e rms_err=%.3e max_ref=%.3f  %s", v3 ? "v3" : (v2 ? "v2" : "v1"), (v2 || v3) ? smem2 : smem, herr, maxerr, sqrt(sumsq / hy.size()), maxref,
            (herr == 0 && maxerr < 1e-4 * (maxref + 1)) ? "OK" : "MISMATCH");
     if (getenv("TC_TRACE") && v3) {
@@ -228,7 +232,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (iters > 0 && herr == 0 && !accum) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        for (int i = 0; i < iters; ++i) { if (v3 && G > 1) b200tts::tc3::grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
+        for (int i = 0; i < iters; ++i) { if (v3 && G > 1) b200tts::tc3::grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3 && a3.stage) b200tts::tc3::conv1d_tc3s_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
         printf("  %.3f ms  %.1f TFLOP/s (algorithmic fp32)", ms, 2.0 * B * Cout * (double)C * K * T / ms / 1e9);

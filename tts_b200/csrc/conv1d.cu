@@ -688,6 +688,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc2::conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         for (int g : {2, 4})
             for (int d : {0, 1, 3, 5})
                 B200_CUDA_OK(cudaFuncSetAttribute(tc3::grouped_kernel(g, d), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -750,9 +751,20 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         t.rows_pad = rows_pad; t.raw_w = rows_pad + 4;
         t.B = io.B; t.n_ttiles = (a.Tq + tc3::TT2 - 1) / tc3::TT2; t.n_rtiles = n_rtiles;
         t.err = g_tc_err;
+        static int staged = -1;
+        if (staged < 0) { const char* e = getenv("B200TTS_STAGED"); staged = (e && atoi(e)) ? 1 : 0; }
+        size_t smem3 = tc3::smem_bytes3(rows_pad, rows_pad + 4);
+        // opt-in (B200TTS_STAGED=1) until it has run through the whole GPU suite: measured in the harness it is 13 % faster
+        // on the epilogue-bound K <= 3 layers and 5-7 % slower on the MMA-bound K = 7 / 11 ones (its shared-memory
+        // traffic competes with the operand fetch), so only short-kernel layers take it
+        if (staged && L.K <= 3 && L.ups == 1 && !t.gate && t.split == 0 && ((smem3 + 15) / 16 * 16 + tc3::STAGE_BYTES) <= 227 * 1024) {
+            t.stage = 1;
+            t.stage_off = (int)((smem3 + 15) / 16 * 16);
+            smem3 = (size_t)t.stage_off + tc3::STAGE_BYTES;
+        }
         const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
         const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-        B200_CUDA_OK(launch_tc3(tc3::conv1d_tc3_kernel, grid, tc3::smem_bytes3(rows_pad, rows_pad + 4), st, t));
+        B200_CUDA_OK(launch_tc3(t.stage ? tc3::conv1d_tc3s_kernel : tc3::conv1d_tc3_kernel, grid, smem3, st, t));
         count_launch();
         B200_CUDA_OK(cudaGetLastError());
         return 0;

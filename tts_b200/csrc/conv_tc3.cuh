@@ -76,6 +76,8 @@ struct Tc3Args {
     int B, n_ttiles, n_rtiles;
     int* err;
     unsigned long long* trace;  // optional [grid][32] globaltimer stamps (debug)
+    int stage;                  // != 0: wide-layer epilogue goes through per-warp shared tiles (coalesced global access)
+    int stage_off;              // byte offset of those tiles in dynamic shared memory (8 warps x 5120 B)
     int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA
 };
 
@@ -111,9 +113,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 
 #define TC3_STAMP(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 32 + (slot)] = gtime(); } while (0)
 
+constexpr int STAGE_BYTES = 8 * 5120;   // staged epilogue: per epilogue warp an output and a residual tile of [32][20] floats
 constexpr int TSTEP_GROUPED = 240;   // 15 chunks of 16 columns: leaves room for the (GRP-1)*dil <= 15 column shift
 
-template <int GRP, int DIL>   // DIL > 0: the layer's dilation as a compile-time constant (windowed TMEM reads in the grouped epilogue)
+template <int GRP, int DIL, bool STAGED = false>   // DIL > 0: the layer's dilation as a compile-time constant (grouped epilogue);
+                                                   // STAGED: wide-layer epilogue through per-warp shared tiles
 __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -528,6 +532,80 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         }
                     }
                 }
+            } else if (STAGED && ups == 1 && a.stage && a.split == 0 && qb + 128 <= a.Tout && ((a.y_cs | a.y_bs) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
+                       (!a.res || ((((a.res_cs | a.res_bs) & 3) == 0) && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0))) {
+                // ---- staged epilogue (interior tiles of wide layers).  With lane = row every float4 LDG / STG of the
+                // direct path touches 32 different cache lines; measured, that L1 wavefront time is not hidden
+                // (profiles/r01_tc_grouped_notes.md).  Here each warp transposes its 32 x 16 block through a private
+                // shared tile: global accesses are 8 rows x 64 contiguous bytes per instruction (4x fewer wavefronts),
+                // the residual arrives by cp.async one column group ahead.
+                const int ew = (warp < 4) ? warp : warp - 6;                       // epilogue warp 0..7
+                float* tO = reinterpret_cast<float*>(smem + a.stage_off) + ew * 1280;   // [32][20]
+                float* tR = tO + 640;
+                const int r8 = lane & 7, p4 = lane >> 3;
+                const int Rbase = rt * MROWS + lq * 32 + r8;                        // + 8*i
+                float* ybase = a.y + (long long)b * a.y_bs + (long long)Rbase * a.y_cs + qb + 4 * p4;
+                const float* rbase = (a.res && !(a.dbg & 4)) ? a.res + (long long)b * a.res_bs + (long long)Rbase * a.res_cs + qb + 4 * p4 : nullptr;
+                const bool acc_r = a.accum != 0 && !(a.dbg & 4), mpost_r = a.mask_post != 0, do_store = !(a.dbg & 8);
+                const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;   // lane = row view (accumulate loads)
+                auto issue_res = [&](int cg) {
+                    if (!rbase) return;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (Rbase + 8 * i < a.Rows)
+                            cp_async16_zfill(smem_u32(tR + (8 * i + r8) * 20 + 4 * p4), rbase + (long long)(8 * i) * a.res_cs + cg, 16u);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                auto prefetch_acc = [&](int cg, float* o_) {
+                    if (!acc_r || !rok) return;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qb + cg + 4 * j));
+                };
+                issue_res(0);
+#pragma unroll 1
+                for (int cg = 0; cg < 128; cg += 16) {
+                    float v[16], ov[16], rv[16];
+                    prefetch_acc(cg, ov);           // accumulate-into-destination (two layers per stage): same-group load
+                    if (rbase) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(tR + lane * 20 + 4 * j);
+                            rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w;
+                        }
+                        __syncwarp();
+                        if (cg + 16 < 128) issue_res(cg + 16);
+                    }
+                    tmem_ld16(dbase + (uint32_t)cg, v);
+                    const int q = qb + cg;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float u = v[i] + bias;
+                        if (a.relu) u = fmaxf(u, 0.f);
+                        const float mk = mrow ? __ldg(mrow + q + i) : 1.f;
+                        if (a.mask_pre) u *= mk;
+                        if (rbase) u += rv[i];
+                        u *= a.scale;
+                        if (acc_r) u += ov[i];
+                        if (a.post_div != 1.f) u = u / a.post_div;
+                        if (mpost_r) u *= mk;
+                        v[i] = u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(tO + lane * 20 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 o4 = *reinterpret_cast<const float4*>(tO + (8 * i + r8) * 20 + 4 * p4);
+                        if (do_store && Rbase + 8 * i < a.Rows) *reinterpret_cast<float4*>(ybase + (long long)(8 * i) * a.y_cs + cg) = o4;
+                    }
+                    __syncwarp();
+                }
             } else if (ups == 1) {
                 float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;
                 bool acc_r = a.accum != 0, mpost_r = a.mask_post != 0;
@@ -632,6 +710,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
 }
 
 __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) { tc3_body<1, 0>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3s_kernel(const Tc3Args a) { tc3_body<1, 0, true>(a); }
 template <int GRP, int DIL>
 __global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g_kernel(const Tc3Args a) { tc3_body<GRP, DIL>(a); }
 
