@@ -193,7 +193,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{nb} of {B_PER_GPU} utterances, {samples} samples per step"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_cuda(args):
@@ -362,12 +362,31 @@ def run_cuda(args):
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{cpu_nb} of {B_PER_GPU} utterances, 1 warm-up + 2 timed steps ({cpu_samples} samples, {cpu_sec:.2f} s per step)"},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's "NCCL version ..." banner under
+    # torchrun, NCCL_DEBUG output) are sent to stderr instead, the result is written to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
