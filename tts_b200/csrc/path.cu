@@ -99,27 +99,27 @@ int launch_expand_prior(const float* cum, const float* x_mask, const long long* 
 // z' = F.interpolate(z, scale_factor=[f], mode="linear") (vits.py:952; align_corners=False): source position
 // (t + 0.5)/f - 0.5 clamped at 0, neighbours t1 and min(t1+1, Tin-1), weights (1-l, l).
 namespace {
-__global__ void upsample_linear_kernel(const float* __restrict__ x, float* __restrict__ y, int Tin, int Tout, float rscale) {
+__global__ void upsample_linear_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int Tin, int Tout,
+                                       float rscale) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Tout) return;
-    const size_t row = blockIdx.y;
     float src = fmaf(rscale, (float)t + 0.5f, -0.5f);   // one rounding, like the reference build's contracted expression
     src = src < 0.f ? 0.f : src;
     const int t1 = (int)src;
     const int t1p = (t1 < Tin - 1) ? 1 : 0;
     const float l1 = src - (float)t1, l0 = 1.f - l1;
-    const float* xr = x + row * Tin;
-    y[row * Tout + t] = fmaf(l1, xr[t1 + t1p], __fmul_rn(l0, xr[t1]));
+    for (size_t row = blockIdx.y; row < (size_t)rows; row += gridDim.y) {
+        const float* xr = x + row * Tin;
+        y[row * Tout + t] = fmaf(l1, xr[t1 + t1p], __fmul_rn(l0, xr[t1]));
+    }
 }
 }  // namespace
 
 int launch_upsample_linear(const float* x, int rows, int Tin, float scale_factor, float* y, int Tout, cudaStream_t st) {
     B200_REQUIRE(x && y && scale_factor > 0.f, "upsample_linear: bad arguments");
     if (rows == 0 || Tout == 0) return 0;
-    B200_REQUIRE(rows <= 65535 * 1024, "upsample_linear: too many rows");
-    dim3 grid((Tout + 255) / 256, rows);
-    B200_REQUIRE(grid.y <= 65535, "upsample_linear: too many rows");
-    upsample_linear_kernel<<<grid, 256, 0, st>>>(x, y, Tin, Tout, (float)(1.0 / (double)scale_factor));
+    dim3 grid((Tout + 255) / 256, rows < 65535 ? rows : 65535);
+    upsample_linear_kernel<<<grid, 256, 0, st>>>(x, y, rows, Tin, Tout, (float)(1.0 / (double)scale_factor));
     count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
