@@ -81,3 +81,47 @@ def test_gather_and_sharded_synthesis_world_size_2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def test_bucket_by_length_partitions_within_budget():
+    from tts_b200.parallel import bucket_by_length
+    lens = [5, 64, 33, 64, 1, 17, 40, 40, 8, 64, 2]
+    buckets = bucket_by_length(lens, max_padded_tokens=128, max_batch=4)
+    assert sorted(i for b in buckets for i in b) == list(range(len(lens)))
+    for b in buckets:
+        assert len(b) <= 4 and len(b) * max(lens[i] for i in b) <= 128
+    # similar lengths end up together: the three 64-token items cannot share a 128-token budget beyond two
+    assert all(len(b) <= 2 for b in buckets if max(lens[i] for i in b) == 64)
+    assert bucket_by_length([], 128, 4) == []
+    assert bucket_by_length([500], 128, 4) == [[0]]          # one over-budget item still gets its own batch
+
+
+def test_synthesize_batched_matches_one_by_one_and_keeps_order():
+    from tts_b200.parallel import concat_sentences, synthesize_batched, to_int16
+    torch.manual_seed(0)
+    model = _FakeVits()
+    seqs = [torch.randint(1, 50, (n,)).tolist() for n in (7, 31, 3, 18, 31, 1, 12)]
+    one_by_one = [model.inference(torch.tensor([s]), {"x_lengths": torch.tensor([len(s)])})["model_outputs"][0, 0]
+                  for s in seqs]
+    got = synthesize_batched(model, seqs, max_padded_tokens=64, max_batch=3)
+    assert len(got) == len(seqs)
+    for a, b in zip(got, one_by_one):
+        assert torch.equal(a, b)
+    speakers = torch.arange(len(seqs))
+
+    class _Spk(_FakeVits):
+        def inference(self, x, aux_input, **kw):
+            out = super().inference(x, aux_input, **kw)
+            out["model_outputs"] = out["model_outputs"] + 1000.0 * aux_input["speaker_ids"].view(-1, 1, 1).float()
+            return out
+
+    got = synthesize_batched(_Spk(), seqs, {"speaker_ids": speakers}, max_padded_tokens=64, max_batch=3)
+    for i, (a, b) in enumerate(zip(got, one_by_one)):
+        assert torch.equal(a, b + 1000.0 * i)                  # conditioning follows its sentence through the buckets
+    cat = concat_sentences(got[:2], gap=10)
+    assert cat.numel() == got[0].numel() + got[1].numel() + 20 and float(cat[got[0].numel():got[0].numel() + 10].abs().sum()) == 0
+    import numpy as np
+    w = torch.randn(1000) * 0.3
+    want = (w.numpy() * (32767 / max(0.01, np.max(np.abs(w.numpy()))))).astype(np.int16)
+    assert np.array_equal(to_int16(w).numpy(), want)
+    assert to_int16(torch.zeros(4)).tolist() == [0, 0, 0, 0]
