@@ -191,7 +191,8 @@ def run_reference(args):
             "config": {"workload": "vits_e2e_inference_b32_t64 (BASELINE configs[1])", "tokens": T_TEXT,
                        "batch_per_gpu": B_PER_GPU, "sample": f"first {nb} of {B_PER_GPU} utterances of the batch per step"},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{nb} of {B_PER_GPU} utterances, {samples} samples per step"},
+                             "sample": f"{nb} of {B_PER_GPU} utterances, {samples} samples per step",
+                             "logical_cpus": os.cpu_count()},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -360,7 +361,8 @@ def run_cuda(args):
                          "frac_of_3xtf32_ceiling": (dec_tflops / (peaks["bf16_tflops_sustained"] / 6.0)) if dec_tflops else None,
                          "frac_fp32_fma": (dec_tflops / FP32_FMA_PEAK_TFLOPS) if dec_tflops else None},
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_nb} of {B_PER_GPU} utterances, 1 warm-up + 2 timed steps ({cpu_samples} samples, {cpu_sec:.2f} s per step)"},
+                             "sample": f"{cpu_nb} of {B_PER_GPU} utterances, 1 warm-up + 2 timed steps ({cpu_samples} samples, {cpu_sec:.2f} s per step)",
+                             "logical_cpus": os.cpu_count()},
         }
         emit(line)
     if world > 1:
