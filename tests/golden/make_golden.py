@@ -125,6 +125,34 @@ def main():
     xmd = seq_mask(torch.tensor([23, 17, 9, 2]), 23)
     save("duration_predictor_small", {"args": args, "state": m.state_dict(), "x": xd, "x_mask": xmd, "g": gd,
                                       "lang_emb": ld, "logw": m(xd, xmd, g=gd, lang_emb=ld)})
+    # 10. voice-conversion chain built from the reference modules (vits.py:1226-1232): posterior encoder -> flow
+    #     forward (source speaker) -> flow reverse (target speaker) -> HiFiGAN
+    hid = 16
+    pe = R["networks"].PosteriorEncoder(33, hid, hid, 5, 1, 3, cond_channels=10).eval()
+    fl = R["networks"].ResidualCouplingBlocks(hid, hid, 5, 1, 2, cond_channels=10).eval()
+    perturb_zero_params(fl)
+    dec = H(hid, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [8, 4], 32, [4, 2], inference_padding=0, cond_channels=10,
+            conv_pre_weight_norm=False, conv_post_weight_norm=False, conv_post_bias=False).eval()
+    yv, lv = torch.randn(2, 33, 21).abs(), torch.tensor([21, 9])
+    g_src, g_tgt = torch.randn(2, 10, 1), torch.randn(2, 10, 1)
+    torch.manual_seed(123)
+    nv = torch.randn(2, hid, 21)
+    torch.manual_seed(123)
+    z, _, _, ym = pe(yv, lv, g=g_src)
+    z_p = fl(z, ym, g=g_src)
+    z_hat = fl(z_p, ym, g=g_tgt, reverse=True)
+    o_hat = dec(z_hat * ym, g=g_tgt)
+    state = {}
+    for prefix, mod in (("posterior_encoder", pe), ("flow", fl), ("waveform_decoder", dec)):
+        state.update({f"{prefix}.{k}": v for k, v in mod.state_dict().items()})
+    save("vc_small", {"state": state, "y": yv, "y_lengths": lv, "g_src": g_src, "g_tgt": g_tgt, "noise": nv,
+                      "z": z, "z_p": z_p, "z_hat": z_hat, "o_hat": o_hat, "y_mask": ym,
+                      "args": {"hidden_channels": hid, "kernel_size_posterior_encoder": 5,
+                               "dilation_rate_posterior_encoder": 1, "num_layers_posterior_encoder": 3,
+                               "kernel_size_flow": 5, "dilation_rate_flow": 1, "num_layers_flow": 2,
+                               "upsample_rates_decoder": [4, 2], "upsample_kernel_sizes_decoder": [8, 4],
+                               "resblock_kernel_sizes_decoder": [3, 7, 11],
+                               "resblock_dilation_sizes_decoder": [[1, 3, 5]] * 3, "resblock_type_decoder": "1"}})
 
 
 if __name__ == "__main__":

@@ -72,6 +72,16 @@ def test_deterministic_duration_predictor(golden):
     assert logw.shape == (4, 1, 23)
 
 
+def test_voice_conversion_chain(golden):
+    """The restated Vits.voice_conversion glue (vits.py:1226-1232) against the same chain run on reference modules."""
+    g = golden("vc_small")
+    o, mask, (z, z_p, z_hat) = O.voice_conversion(g["state"], g["y"], g["y_lengths"], g["g_src"], g["g_tgt"], g["noise"],
+                                                   args=g["args"])
+    assert torch.equal(mask, g["y_mask"])
+    for got, key in ((z, "z"), (z_p, "z_p"), (z_hat, "z_hat"), (o, "o_hat")):
+        assert torch.equal(got, g[key]), key
+
+
 def test_mas_ports_match_reference_kernel(golden):
     for case in golden("mas_cases")["cases"]:
         for impl in ("c", "py"):
