@@ -27,10 +27,17 @@ T_TEXT = 64
 SR = 22050
 HIFIGAN_FLOP_PER_SAMPLE = 2.402e6      # SURVEY.md section 8d (Cin=192)
 FLOW_FLOP_PER_FRAME = 14.16e6
-FP32_FMA_PEAK_TFLOPS = 73.5            # measured on this pool with tools/microbench_fma.cu (FFMA2), see DESIGN.md
-# dram__bytes_read+write summed over the 78 conv launches of one HiFiGAN pass at this workload's shape (B=32, 192
-# padded frames), from one ncu capture: profiles/r01_decoder_dram_traffic_final.csv (19.79 GB read + 8.89 GB written)
-DECODER_DRAM_BYTES_PER_PASS = {6144: 28.68e9}
+
+
+def load_measured(name, default=None):
+    """Numbers that only a GPU box can produce are committed under profiles/ by the run that measured them
+    (profiles/measured.json: FP32-FMA and dense-TF32 peaks from tools/microbench_*.cu, DRAM bytes of a decoder pass
+    per shape from an ncu capture); nothing here is a hand-typed constant.  Missing key -> `default` (None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "measured.json")) as f:
+            return json.load(f).get(name, default)
+    except Exception:
+        return default
 
 
 def load_peaks():
@@ -153,11 +160,18 @@ def host_threads():
     return max(1, n)
 
 
-def cpu_reference_samples_per_s(nbatch, steps=1, warmup=0, threads=None):
-    """The reference's CPU algorithm (oracle port, bit-identical to the reference modules) on host cores."""
-    import torch
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vits_oracle as O
+    return O
+
+
+def cpu_reference_samples_per_s(nbatch, steps=1, warmup=0, threads=None, first_noise=None):
+    """The reference's CPU algorithm (oracle port, bit-identical to the reference modules) on host cores.
+    ``first_noise``: prior-noise tensor for the FIRST (warm-up) pass -- the parity gate feeds the GPU step's own
+    draw here and compares that pass's output; returns (samples/s, s/step, samples, threads, first_output)."""
+    import torch
+    O = _oracle()
     from dataclasses import asdict
     # every host thread the container may use (torchrun exports OMP_NUM_THREADS=1; override it at run time)
     torch.set_num_threads(threads or host_threads())
@@ -167,16 +181,22 @@ def cpu_reference_samples_per_s(nbatch, steps=1, warmup=0, threads=None):
     tokens, lengths, sdp_noise = make_batch(0)
     tokens, lengths, sdp_noise = tokens[:nbatch], lengths[:nbatch], sdp_noise[:nbatch]
     gen = torch.Generator().manual_seed(7)
-    times, samples = [], 0
+    times, samples, first = [], 0, None
     with torch.no_grad():
         for i in range(warmup + steps):
+            def noise_fn(shape, i=i):
+                if i == 0 and first_noise is not None and tuple(shape) == tuple(first_noise[:nbatch].shape):
+                    return first_noise[:nbatch]
+                return torch.randn(shape, generator=gen)
             t0 = time.perf_counter()
-            out = O.vits_inference(sd, tokens, lengths, sdp_noise, lambda s: torch.randn(s, generator=gen), args=args)
+            out = O.vits_inference(sd, tokens, lengths, sdp_noise, noise_fn, args=args)
             dt = time.perf_counter() - t0
+            if i == 0:
+                first = out
             if i >= warmup:
                 times.append(dt)
                 samples = int(out["y_lengths"].sum()) * 256
-    return samples / (sum(times) / len(times)), sum(times) / len(times), samples, torch.get_num_threads()
+    return samples / (sum(times) / len(times)), sum(times) / len(times), samples, torch.get_num_threads(), first
 
 
 def run_reference(args):
@@ -184,7 +204,7 @@ def run_reference(args):
     if rank != 0:
         return
     nb = B_PER_GPU if host_threads() >= 8 else 4          # the whole batch per step when the host can afford it
-    v, sec, samples, cores = cpu_reference_samples_per_s(nb, steps=args.steps, warmup=args.warmup)
+    v, sec, samples, cores, _ = cpu_reference_samples_per_s(nb, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "audio_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -195,6 +215,153 @@ def run_reference(args):
                              "logical_cpus": os.cpu_count()},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def parity_report(got, want, nb):
+    """The parity gate of the measured workload: the GPU step's outputs against the oracle's on the same tokens and
+    the same random draws (north_star: MAS/duration indices bit-exact, waveform within 1e-4 RMS)."""
+    import torch
+    g = {k: (v[:nb].detach().float().cpu() if torch.is_tensor(v) else v) for k, v in got.items()}
+    w = want
+    rep = {"utterances": nb,
+           "durations_equal": bool(torch.equal(g["durations"], w["durations"])),
+           "y_lengths_equal": bool(torch.equal(got["y_lengths"][:nb].cpu(), w["y_lengths"]))}
+    tw = w["alignments"].shape[-1]
+    rep["path_equal"] = bool(g["alignments"].shape[-1] >= tw and torch.equal(g["alignments"][..., :tw], w["alignments"])
+                             and float(g["alignments"][..., tw:].abs().sum()) == 0.0)
+    n = w["model_outputs"].shape[-1]
+    if g["model_outputs"].shape[-1] >= n:
+        err = g["model_outputs"][..., :n] - w["model_outputs"]
+        # compare the samples every caller keeps (valid lengths); the padded tail is reported separately
+        valid = (torch.arange(n)[None, None, :] < (w["y_lengths"] * 256)[:, None, None]).float()
+        nv = float(valid.sum())
+        rms = float(((err * valid) ** 2).sum() / nv) ** 0.5
+        ref_rms = float(((w["model_outputs"] * valid) ** 2).sum() / nv) ** 0.5
+        rep.update({"wav_rms": rms, "wav_rel_rms": rms / max(ref_rms, 1e-30), "wav_ref_rms": ref_rms,
+                    "wav_max_abs": float((err * valid).abs().max()),
+                    "wav_rms_padded_tail": float((((err * (1 - valid)) ** 2).sum() / max(float((1 - valid).sum()), 1.0)) ** 0.5)})
+        z_err = float((g["z"][..., :tw] - w["z"]).abs().max()) if g["z"].shape[-1] >= tw else None
+        rep["z_max_abs"] = z_err
+        rep["ok"] = bool(rep["durations_equal"] and rep["path_equal"] and rep["y_lengths_equal"] and rms <= 1e-4
+                         and rep["wav_rel_rms"] <= 1e-4)
+    else:
+        rep["ok"] = False
+    return rep
+
+
+def gpu_eager_baseline(dev, steps=3):
+    """The bar SURVEY 2a names: the same algorithm as PyTorch eager library kernels (cuDNN / cuBLAS) on the GPU, TF32
+    off (fp32 like the reference), same batch and noise.  It is the oracle port moved to the device -- measured
+    outside the product arm's timed region, reported beside it, never on the product path."""
+    import torch
+    O = _oracle()
+    from dataclasses import asdict
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model = build_model()
+        sd = {k: v.to(dev) for k, v in model.state_dict().items()}
+        args = asdict(model.args)
+        tokens, lengths, sdp_noise = (t.to(dev) for t in make_batch(0))
+        gen = torch.Generator(device=dev).manual_seed(7)
+        fn = lambda shape: torch.randn(shape, generator=gen, device=dev)
+        ev = []
+        samples = 0
+        with torch.no_grad():
+            for i in range(1 + steps):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = O.vits_inference(sd, tokens, lengths, sdp_noise, fn, args=args)
+                e.record()
+                if i > 0:
+                    ev.append((s, e))
+                    samples += int(out["y_lengths"].sum()) * 256
+        torch.cuda.synchronize()
+        sec = sum(s.elapsed_time(e) for s, e in ev) / 1e3
+        return {"value": samples / sec, "unit": "samples/s", "ms_per_step": sec / steps * 1e3,
+                "kind": "oracle port on cuda (torch eager: cuDNN conv / cuBLAS matmul), allow_tf32=False",
+                "steps": steps, "warmup": 1}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def secondary_results(dev, peaks):
+    """Sub-results on the other BASELINE configs that fit one GPU (not the headline; same JSON line, key `secondary`):
+    cfg3 per-GPU shard (flow reverse + HiFiGAN, B=32, 1024 frames), cfg4 MAS (512 x 200 x 1000), cfg5 multi-speaker
+    B=128 mixed lengths.  CUDA events, 1 warm-up + 3 timed passes each, L2 flushed between passes."""
+    import torch
+    from tts_b200.helpers import maximum_path
+    from tts_b200.vits import Vits, VitsArgs, VitsConfig
+    res = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, n=3):
+        fn()
+        ts = []
+        for _ in range(n):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sum(ts) / len(ts)
+
+    try:   # cfg3 shard
+        model = build_model().to(dev)
+        g = torch.Generator(device=dev).manual_seed(3)
+        z_p = torch.randn(32, 192, 1024, generator=g, device=dev)
+        mask = torch.ones(32, 1, 1024, device=dev)
+        ms_flow = timed(lambda: model.flow(z_p, mask, reverse=True))
+        z = model.flow(z_p, mask, reverse=True)
+        ms_dec = timed(lambda: model.waveform_decoder(z))
+        n = 32 * 1024 * 256
+        res["cfg3_shard_flow_hifigan_b32_t1024"] = {
+            "flow_ms": ms_flow, "hifigan_ms": ms_dec, "samples_per_s": n / ((ms_flow + ms_dec) / 1e3),
+            "hifigan_tflops": n * HIFIGAN_FLOP_PER_SAMPLE / (ms_dec / 1e3) / 1e12,
+            "flow_tflops": 32 * 1024 * FLOW_FLOP_PER_FRAME / (ms_flow / 1e3) / 1e12}
+        del z_p, z, mask
+    except Exception as ex:  # noqa: BLE001 - a sub-result must not take the headline down
+        res["cfg3_shard_flow_hifigan_b32_t1024"] = {"error": repr(ex)[:200]}
+    try:   # cfg4 MAS
+        g = torch.Generator(device=dev).manual_seed(4)
+        v = torch.randn(512, 200, 1000, generator=g, device=dev)
+        m = torch.ones(512, 200, 1000, device=dev)
+        from tts_b200.helpers import maximum_path_lengths
+        tx = torch.full((512,), 200, dtype=torch.int32, device=dev)
+        ty = torch.full((512,), 1000, dtype=torch.int32, device=dev)
+        ms = timed(lambda: maximum_path_lengths(v, tx, ty))
+        gbs = 512 * 200 * 1000 * 8 / (ms / 1e3) / 1e9
+        res["cfg4_mas_b512_200x1000"] = {"ms": ms, "gbs": gbs, "frac_hbm": gbs / peaks["hbm_gbs"],
+                                         "bytes": "8 B per cell (f32 value in, i32 path out)"}
+        del v, m
+    except Exception as ex:  # noqa: BLE001
+        res["cfg4_mas_b512_200x1000"] = {"error": repr(ex)[:200]}
+    try:   # cfg5
+        torch.manual_seed(1234)
+        cfg = VitsConfig(model_args=VitsArgs(use_speaker_embedding=True, num_speakers=109))
+        m5 = Vits(cfg).eval().to(dev)
+        gen = torch.Generator().manual_seed(55)
+        lens = torch.randint(20, 129, (128,), generator=gen)
+        tok = torch.randint(0, 100, (128, 128), generator=gen)
+        tok = tok * (torch.arange(128)[None, :] < lens[:, None])
+        sid = torch.randint(0, 109, (128,), generator=gen)
+        noise = torch.randn(128, 2, 128, generator=gen).to(dev)
+        tok_d, lens_d, sid_d = tok.to(dev), lens.to(dev), sid.to(dev)
+        out = {}
+
+        def step():
+            out["o"] = m5.inference(tok_d, {"x_lengths": lens_d, "speaker_ids": sid_d}, sdp_noise=noise)
+        ms = timed(step)
+        n = int(out["o"]["wav_lengths"].sum())
+        res["cfg5_multispeaker_b128_mixed"] = {"ms": ms, "samples_per_s": n / (ms / 1e3), "valid_samples": n,
+                                               "frames_padded": int(out["o"]["y_mask"].shape[-1]) * 128}
+    except Exception as ex:  # noqa: BLE001
+        res["cfg5_multispeaker_b128_mixed"] = {"error": repr(ex)[:200]}
+    return res
 
 
 def run_cuda(args):
@@ -218,23 +385,36 @@ def run_cuda(args):
     tokens_d, lengths_d, noise_d = tokens_h.to(dev), lengths_h.to(dev), sdp_noise_h.to(dev)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gatherer = None
+    if world > 1:
+        from tts_b200.parallel import WaveformGather
+        gatherer = WaveformGather(dev, dst=0)
+    gather_ev = []
 
     def prior_noise(shape):
         return torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
 
-    def gather(wav, y_lengths):
+    def gather(out, timed=False):
         if world == 1:
             return
-        # the one collective on the data path: rank 0 gathers the (padded) waveforms + lengths over NVLink
-        from tts_b200.parallel import gather_waveforms
-        gather_waveforms(wav, y_lengths * 256, dst=0)
+        # the one collective on the data path: rank 0 receives every rank's padded waveforms + valid lengths over
+        # NVLink.  Shapes are exchanged as host integers on a side stream, the payload follows the decoder there;
+        # the step's end event waits for it (current stream <- side stream), so the timed region contains it.
+        if timed:
+            a = torch.cuda.Event(enable_timing=True)
+            a.record()
+        gatherer.gather(out["model_outputs"], out["wav_lengths"]).wait()
+        if timed:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            gather_ev.append((a, b))
 
     def step_resident(stage_events=None):
         model._stage_events = stage_events
         out = model.inference(tokens_d, {"x_lengths": lengths_d}, sdp_noise=noise_d, prior_noise=prior_noise,
                               return_alignments=True)
         model._stage_events = None
-        gather(out["model_outputs"], out["y_lengths"])
+        gather(out, timed=stage_events is not None)
         return out
 
     host_wav = {}
@@ -244,14 +424,14 @@ def run_cuda(args):
         ln = lengths_pin.to(dev, non_blocking=True)
         nz = noise_pin.to(dev, non_blocking=True)
         out = model.inference(tok, {"x_lengths": ln}, sdp_noise=nz, prior_noise=prior_noise, return_alignments=True)
-        gather(out["model_outputs"], out["y_lengths"])
+        gather(out)
         wav = out["model_outputs"]
         key = tuple(wav.shape)
         if key not in host_wav:
             host_wav[key] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
         host_wav[key].copy_(wav, non_blocking=True)
-        yl = out["y_lengths"].cpu()  # device->host read of the step's result (also synchronises)
-        return out, wav.numel() * 4 + yl.numel() * 8
+        yl = out["wav_lengths"].cpu()  # device->host read of the step's result (also synchronises)
+        return out, wav.numel() * 4 + yl.numel() * 8, int(yl.sum())
 
     def barrier():
         if world > 1:
@@ -271,7 +451,7 @@ def run_cuda(args):
     launches0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_ev = []
-    samples_rank = 0
+    lens_out = []
     padded_samples = 0
     frames_padded = 0
     barrier()
@@ -281,10 +461,11 @@ def run_cuda(args):
         s.record()
         out = step_resident(stage_ev)
         e.record()
-        samples_rank += int(out["y_lengths"].sum().item()) * 256
+        lens_out.append(out["wav_lengths"])          # read after the loop: no extra host sync inside a step
         padded_samples += out["model_outputs"].numel()
         frames_padded += out["y_mask"].shape[0] * out["y_mask"].shape[-1]
     barrier()
+    samples_rank = int(sum(int(l.sum().item()) for l in lens_out))
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop(first_sample)
     t_resident = sum(s.elapsed_time(e) for s, e in ev) / 1e3
@@ -292,9 +473,12 @@ def run_cuda(args):
     stage_ms = {}
     for n, a, b in stage_ev:
         stage_ms[n] = stage_ms.get(n, 0.0) + a.elapsed_time(b)
+    gather_ms = sum(a.elapsed_time(b) for a, b in gather_ev)
     if os.environ.get("BENCH_DEBUG") and rank == 0:
         print("per-step ms:", [round(s.elapsed_time(e), 2) for s, e in ev], file=sys.stderr)
         print("per-stage:", [(n, round(a.elapsed_time(b), 2)) for n, a, b in stage_ev], file=sys.stderr)
+    if _lib.lib().b200tts_debug_tc_error():
+        raise RuntimeError("bench: a tcgen05 conv launch hit a pipeline timeout -- results are invalid")
 
     # ---------------- timed region 2: end to end from pinned host buffers
     for _ in range(2):
@@ -303,28 +487,45 @@ def run_cuda(args):
     t0 = time.perf_counter()
     e2e_samples, d2h = 0, 0
     for _ in range(args.steps):
-        out, nbytes = step_e2e()
-        e2e_samples += int(out["y_lengths"].sum().item()) * 256
+        out, nbytes, nvalid = step_e2e()
+        e2e_samples += nvalid
         d2h = nbytes
     barrier()
     t_e2e = time.perf_counter() - t0
 
-    def allmax(x):
+    def allred(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    allmax = lambda x: allred(x, dist.ReduceOp.MAX)
+    allsum = lambda x: allred(x, dist.ReduceOp.SUM)
     t_resident_max, t_e2e_max = allmax(t_resident), allmax(t_e2e)
     total_samples, total_e2e_samples = allsum(samples_rank), allsum(e2e_samples)
+    frames_max, frames_sum = allmax(frames_padded / args.steps), allsum(frames_padded / args.steps)
+    compute_ms_max = allmax((t_resident * 1e3 - gather_ms) / args.steps)
+    compute_ms_sum = allsum((t_resident * 1e3 - gather_ms) / args.steps)
+    gather_ms_max = allmax(gather_ms / args.steps)
+
+    # ---------------- parity gate of the measured workload (rank 0, N = 1): same tokens, same draws, vs the oracle
+    parity, cpu = None, None
+    if rank == 0 and world == 1 and not os.environ.get("BENCH_SKIP_CPU"):
+        store = {}
+
+        def fixed_noise(shape):
+            store["n"] = torch.randn(shape, generator=torch.Generator().manual_seed(777))
+            return store["n"].to(dev)
+
+        got = model.inference(tokens_d, {"x_lengths": lengths_d}, sdp_noise=noise_d, prior_noise=fixed_noise)
+        torch.cuda.synchronize()
+        cpu_nb = B_PER_GPU if host_threads() >= 8 else 2
+        cpu_v, cpu_sec, cpu_samples, cores, first = cpu_reference_samples_per_s(cpu_nb, steps=2, warmup=1,
+                                                                                 first_noise=store["n"])
+        cpu = (cpu_nb, cpu_v, cpu_sec, cpu_samples, cores)
+        parity = parity_report(got, first, cpu_nb)
+        del got
 
     if rank == 0:
         peaks = load_peaks()
@@ -332,11 +533,21 @@ def run_cuda(args):
         e2e_value = total_e2e_samples / t_e2e_max
         dec_tflops = padded_samples * HIFIGAN_FLOP_PER_SAMPLE / (dec_ms / 1e3) / 1e12 if dec_ms > 0 else None
         h2d = tokens_pin.numel() * 8 + lengths_pin.numel() * 8 + noise_pin.numel() * 4
-        if os.environ.get("BENCH_SKIP_CPU"):   # developer A/B runs only: the contract line always carries cpu_baseline
-            cpu_nb, cpu_v, cpu_sec, cpu_samples, cores = 0, float("nan"), 0.0, 0, 0
+        if cpu is None:   # developer A/B runs (BENCH_SKIP_CPU) and N > 1: the contract's cpu_baseline is an N = 1 item
+            cpu_nb, cpu_v, cpu_sec, cpu_samples, cores = 0, None, 0.0, 0, 0
         else:
-            cpu_nb = B_PER_GPU if host_threads() >= 8 else 2
-            cpu_v, cpu_sec, cpu_samples, cores = cpu_reference_samples_per_s(cpu_nb, steps=2, warmup=1)
+            cpu_nb, cpu_v, cpu_sec, cpu_samples, cores = cpu
+        tf32_peak = load_measured("tf32_dense_tflops")          # tools/microbench_mma.cu on this pool (None: not measured)
+        fma_peak = load_measured("fp32_fma_tflops")
+        traffic = (load_measured("decoder_dram_bytes_per_pass") or {}).get(str(frames_padded // args.steps))
+        eager = None
+        secondary = None
+        if world == 1 and not os.environ.get("BENCH_SKIP_EXTRA"):
+            try:
+                eager = gpu_eager_baseline(dev)
+            except Exception as ex:  # noqa: BLE001
+                eager = {"error": repr(ex)[:200]}
+            secondary = secondary_results(dev, peaks)
         line = {
             "metric": "audio_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_resident_max / args.steps * 1e3,
@@ -345,24 +556,33 @@ def run_cuda(args):
                        "tokens": T_TEXT, "frames_padded_per_step": frames_padded // args.steps,
                        "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps (outside the events)",
                        "rtf": (t_resident_max / args.steps) / (total_samples / args.steps / SR),
-                       "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}},
+                       "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                       "multi_gpu": None if world == 1 else {
+                           "compute_ms_per_step_max": compute_ms_max, "compute_ms_per_step_mean": compute_ms_sum / world,
+                           "gather_wait_ms_per_step_max": gather_ms_max,
+                           "padded_frames_per_rank_max": frames_max, "padded_frames_per_rank_mean": frames_sum / world,
+                           "note": "ranks synthesise different random batches; max/mean padded frames is the work skew "
+                                   "the max-over-ranks time contains"}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv1d_tc3_kernel + conv1d_tc3g_kernel<GRP,DIL> + conv1d_row1_kernel (the 78 HiFiGAN launches of a step; conv1d_tc3_kernel alone is 56 % of the step)",
+            "parity": parity,
+            "roofline": {"bound": "tensor", "kernel": "HiFiGAN decoder pass (tcgen05 3xTF32 conv kernels + conv_post)",
                          "achieved": dec_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (dec_tflops / peaks["bf16_tflops_sustained"]) if dec_tflops else None,
-                         "traffic": DECODER_DRAM_BYTES_PER_PASS.get(frames_padded // args.steps),
-                         "traffic_unit": "bytes per decoder pass (78 launches), ncu dram__bytes_read+write; algorithmic layer-granular = 21.2 KB/sample",
+                         "traffic": traffic,
+                         "traffic_unit": "bytes per decoder pass, ncu dram__bytes_read+write (profiles/measured.json, keyed by padded frames); algorithmic layer-granular = 21.2 KB/sample",
                          "peak_source": peaks["source"],
-                         "note": "algorithmic fp32 FLOPs; the MRF/pre convs run on tcgen05 kind::tf32 as 3xTF32 (3 MMAs per "
-                                 "algorithmic MAC at half the bf16 rate => ceiling = peak/6); conv_post is a streaming FP32 kernel "
-                                 f"(FP32 FMA peak measured {FP32_FMA_PEAK_TFLOPS} TFLOP/s)",
-                         "frac_of_3xtf32_ceiling": (dec_tflops / (peaks["bf16_tflops_sustained"] / 6.0)) if dec_tflops else None,
-                         "frac_fp32_fma": (dec_tflops / FP32_FMA_PEAK_TFLOPS) if dec_tflops else None},
+                         "note": "algorithmic fp32 FLOPs; the convs run on tcgen05 kind::tf32 as 3xTF32 (3 MMAs per "
+                                 "algorithmic MAC) => ceiling = dense TF32 peak / 3; conv_post is a streaming FP32 kernel",
+                         "tf32_dense_peak_measured": tf32_peak,
+                         "frac_of_3xtf32_ceiling": (dec_tflops / (tf32_peak / 3.0)) if (dec_tflops and tf32_peak) else None,
+                         "frac_fp32_fma": (dec_tflops / fma_peak) if (dec_tflops and fma_peak) else None},
             "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_nb} of {B_PER_GPU} utterances, 1 warm-up + 2 timed steps ({cpu_samples} samples, {cpu_sec:.2f} s per step)",
+                             "sample": f"{cpu_nb} of {B_PER_GPU} utterances, 1 warm-up (= the parity pass) + 2 timed steps ({cpu_samples} samples, {cpu_sec:.2f} s per step)",
                              "logical_cpus": os.cpu_count()},
+            "gpu_eager_baseline": eager,
+            "secondary": secondary,
         }
         emit(line)
     if world > 1:

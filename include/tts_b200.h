@@ -30,8 +30,39 @@ const char* b200tts_last_error(void);
 /* number of kernels launched by this library in this process (bench.py "gpu_launches") */
 unsigned long long b200tts_launch_count(void);
 int b200tts_version(void);
-/* debug aid: 1 if a tcgen05 conv launch ever hit a pipeline timeout (synchronises the device) */
+/* 1 if a tcgen05 conv launch (on any device of this process) ever hit a pipeline timeout.  The flag lives in mapped
+ * host memory: no synchronisation here (call after a stream sync to cover the launches before it).  Every later
+ * conv launch on that device also checks it and returns status 1, so a timeout cannot pass silently. */
 int b200tts_debug_tc_error(void);
+
+/* Debug / test aids: record, on the calling thread, which kernel family every conv launch dispatched to.
+ * ids: 0 FP32-FMA tile kernel, 1 tcgen05 v1, 2 tcgen05 v2 (M = time), 3 tcgen05 v3 (M = rows), 4 v3 + staged epilogue,
+ *      5 v3 grouped (narrow layers), 6 single-row streaming kernel (conv_post), 7 fused ResBlock kernel. */
+void b200tts_debug_dispatch_begin(void);
+int b200tts_debug_dispatch_end(int32_t* ids, int cap); /* returns the number of launches recorded */
+
+/* ---- one conv layer with the fused prologue / epilogue the engines use -------------------------
+ * The building block every dense contraction of the path runs on; replaces one
+ * F.conv1d / F.conv_transpose1d call together with the element-wise ops around it, e.g. the ResBlock1 step
+ * `xt = F.leaky_relu(x, 0.1); xt = c1(xt)` ... `x = xt + x` (TTS/vocoder/models/hifigan_generator.py:93-99) or
+ * `o = self.ups[i](F.leaky_relu(o, 0.1))` (:248-249):
+ *   y = ((conv(leaky_relu(x, in_slope)) + bias) + residual) * scale [+ y_old if accumulate] / post_div
+ * weight: host, PyTorch layout ([Cout,Cin,K], or [Cin,Cout,K] when transposed); bias host or NULL; x [B,Cin,T],
+ * residual / y [B,Cout,Tout] device.  in_slope = 1 disables the prologue.  allow_tensor_cores != 0 opts the layer into
+ * the tcgen05 3xTF32 kernels (the decoder / flow setting); 0 keeps it on the exact FP32-FMA kernel (text encoder).
+ */
+typedef struct {
+    int in_channels, out_channels, kernel_size, dilation, padding;
+    int transposed; /* 1: ConvTranspose1d with `stride` (dilation must be 1) */
+    int stride;
+} b200tts_conv1d_config;
+typedef struct b200tts_conv1d b200tts_conv1d;
+int b200tts_conv1d_create(const b200tts_conv1d_config* cfg, const float* weight, const float* bias,
+                          int allow_tensor_cores, b200tts_conv1d** out);
+void b200tts_conv1d_destroy(b200tts_conv1d* h);
+int b200tts_conv1d_out_len(const b200tts_conv1d* h, int T);
+int b200tts_conv1d_forward(const b200tts_conv1d* h, const float* x, int B, int T, float in_slope, const float* residual,
+                           float scale, int accumulate, float post_div, float* y, void* stream);
 
 /* ---- monotonic alignment search ------------------------------------------------------------
  * Replaces maximum_path_c / maximum_path_each, TTS/tts/utils/monotonic_align/core.pyx:11-47
@@ -234,13 +265,15 @@ int b200tts_sdp_reverse(const b200tts_sdp* h, const float* x, const float* mask,
 /* ---- durations -> path -> expanded prior ------------------------------------------------------
  * Replaces the glue at TTS/tts/models/vits.py:1140-1155 (generate_path: TTS/tts/utils/helpers.py:154-169).
  * b200tts_durations : w_ceil [B,T] = ceil(exp(logw) * x_mask * length_scale); cum [B,T] = cumsum(w_ceil);
- *                     y_lengths int64 [B] = max(1, sum(w_ceil)).
+ *                     y_lengths int64 [B] = max(1, sum(w_ceil)); meta int64 [2] (or NULL) = {max_b y_lengths,
+ *                     *err_flag (the duration predictor's spline flag, may be NULL -> 0)}: the one host read of
+ *                     Vits.inference (sequence_mask(y_lengths, None), helpers.py:53-54) fetches both.
  * b200tts_expand_prior (after the caller has read max(y_lengths) = Ty): attn [B,Tx,Ty] one-hot (or NULL),
  *   m_p / logs_p / z_p [B,C,Ty] with z_p = m_p + noise * exp(logs_p) * noise_scale, y_mask [B,Ty] (or NULL);
  *   stats is the text encoder's [B,2C,Tx]; noise [B,C,Ty] is the randn_like(m_p) draw of vits.py:1155.
  */
 int b200tts_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
-                      float* cum, int64_t* y_lengths, void* stream);
+                      float* cum, int64_t* y_lengths, const int32_t* err_flag, int64_t* meta, void* stream);
 int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y_lengths, const float* stats,
                          const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn,
                          float* m_p, float* logs_p, float* z_p, float* y_mask, void* stream);

@@ -188,7 +188,7 @@ def rel_attention(sd, x, attn_mask, *, num_heads, window):
     if window is not None:
         ek, ev = sd["emb_rel_k"], sd["emb_rel_v"]  # [1 or H, 2w+1, d]
         rel = torch.matmul(q, ek.unsqueeze(0).transpose(-2, -1)) / math.sqrt(d)  # [b,h,t,2w+1]
-        idx = torch.arange(t)
+        idx = torch.arange(t, device=x.device)
         off = idx[None, :] - idx[:, None] + window  # j - i + w
         valid = (off >= 0) & (off <= 2 * window)
         gathered = torch.gather(rel, 3, off.clamp(0, 2 * window).expand(b, num_heads, t, t))
@@ -197,7 +197,7 @@ def rel_attention(sd, x, attn_mask, *, num_heads, window):
     p = F.softmax(scores, dim=-1)
     out = torch.matmul(p, v)
     if window is not None:
-        pw = torch.zeros(b, num_heads, t, 2 * window + 1, dtype=p.dtype)
+        pw = torch.zeros(b, num_heads, t, 2 * window + 1, dtype=p.dtype, device=p.device)
         for r in range(2 * window + 1):
             j = idx + (r - window)
             ok = (j >= 0) & (j < t)

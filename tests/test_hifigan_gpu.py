@@ -18,6 +18,8 @@ def _close(got, want):
     err = got - want
     rms = err.pow(2).mean().sqrt().item()
     assert rms <= RMS_TOL and err.abs().max().item() <= MAX_TOL, (rms, err.abs().max().item(), want.abs().max().item())
+    ref = want.pow(2).mean().sqrt().item()
+    assert rms <= 1e-4 * ref, f"relative RMS error {rms / ref} (signal RMS {ref})"
 
 
 def _build(args):

@@ -34,7 +34,8 @@ class _FakeVits(torch.nn.Module):
         for b in range(x.shape[0]):
             n = int(y_lengths[b]) * 4
             wav[b, 0, :n] = float(x[b, : int(lens[b])].sum()) + torch.arange(n)
-        return {"model_outputs": wav, "y_lengths": y_lengths, "y_mask": torch.ones(x.shape[0], 1, t)}
+        return {"model_outputs": wav, "y_lengths": y_lengths, "y_mask": torch.ones(x.shape[0], 1, t),
+                "wav_lengths": y_lengths * 4}
 
 
 def _worker(rank, world, port, q):

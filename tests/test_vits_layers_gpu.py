@@ -215,8 +215,9 @@ def test_durations_and_path_expansion_bit_exact_vs_oracle():
         logs_p = torch.matmul(attn.transpose(1, 2), stats[:, c:].transpose(1, 2)).transpose(1, 2)
         noise = torch.randn_like(m_p)
         z_p = m_p + noise * torch.exp(logs_p) * 0.667
-        gw, gcum, gy = durations_to_path(logw.cuda(), mask.cuda(), length_scale)
+        gw, gcum, gy, meta = durations_to_path(logw.cuda(), mask.cuda(), length_scale)
         assert torch.equal(gw.cpu(), w_ceil) and torch.equal(gy.cpu(), y_len)
+        assert meta.tolist() == [int(y_len.max()), 0]
         t_dec = int(gy.max())
         ga, gm, gl, gz, gym = expand_prior(gcum, mask.cuda(), gy, stats.cuda(), noise.cuda(), 0.667, t_dec)
         assert torch.equal(ga.cpu(), attn) and torch.equal(gym.cpu(), y_mask)

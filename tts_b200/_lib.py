@@ -57,11 +57,31 @@ class DurationPredictorConfigC(ctypes.Structure):
                                             "language_emb_dim")]
 
 
+class Conv1dConfigC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("in_channels", "out_channels", "kernel_size", "dilation", "padding",
+                                            "transposed", "stride")]
+
+
+DISPATCH_NAMES = {0: "fma", 1: "tc1", 2: "tc2", 3: "tc3", 4: "tc3_staged", 5: "tc3_grouped", 6: "row1", 7: "resblock"}
+
+
 def _declare(lib):
     vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     lib.b200tts_last_error.restype = ctypes.c_char_p
     lib.b200tts_launch_count.restype = ctypes.c_ulonglong
     lib.b200tts_version.restype = ci
+    lib.b200tts_debug_tc_error.restype = ci
+    lib.b200tts_debug_dispatch_begin.restype = None
+    lib.b200tts_debug_dispatch_end.restype = ci
+    lib.b200tts_debug_dispatch_end.argtypes = [vp, ci]
+    lib.b200tts_conv1d_create.restype = ci
+    lib.b200tts_conv1d_create.argtypes = [ctypes.POINTER(Conv1dConfigC), vp, vp, ci, ctypes.POINTER(vp)]
+    lib.b200tts_conv1d_destroy.restype = None
+    lib.b200tts_conv1d_destroy.argtypes = [vp]
+    lib.b200tts_conv1d_out_len.restype = ci
+    lib.b200tts_conv1d_out_len.argtypes = [vp, ci]
+    lib.b200tts_conv1d_forward.restype = ci
+    lib.b200tts_conv1d_forward.argtypes = [vp, vp, ci, ci, ctypes.c_float, vp, ctypes.c_float, ci, ctypes.c_float, vp, vp]
     lib.b200tts_mas_workspace_bytes.restype = sz
     lib.b200tts_mas_workspace_bytes.argtypes = [ci, ci, ci]
     lib.b200tts_mas.restype = ci
@@ -112,7 +132,7 @@ def _declare(lib):
     lib.b200tts_sdp_reverse.restype = ci
     lib.b200tts_sdp_reverse.argtypes = [vp, vp, vp, vp, vp, vp, cf, ci, ci, vp, vp, vp, sz, vp]
     lib.b200tts_durations.restype = ci
-    lib.b200tts_durations.argtypes = [vp, vp, cf, ci, ci, vp, vp, vp, vp]
+    lib.b200tts_durations.argtypes = [vp, vp, cf, ci, ci, vp, vp, vp, vp, vp, vp]
     lib.b200tts_expand_prior.restype = ci
     lib.b200tts_expand_prior.argtypes = [vp, vp, vp, vp, vp, cf, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
 
@@ -149,6 +169,21 @@ def require_cuda(t, name):
     if not t.is_cuda:
         raise RuntimeError(f"tts_b200: `{name}` must be a CUDA tensor -- this package has no CPU path")
     return t
+
+
+class dispatch_log:
+    """``with dispatch_log() as log: ...`` -> ``log.names``: the kernel family of every conv launch inside the block."""
+
+    def __enter__(self):
+        lib().b200tts_debug_dispatch_begin()
+        self.names = []
+        return self
+
+    def __exit__(self, *exc):
+        buf = (ctypes.c_int32 * 4096)()
+        n = lib().b200tts_debug_dispatch_end(buf, 4096)
+        self.names = [DISPATCH_NAMES.get(int(buf[i]), str(int(buf[i]))) for i in range(min(n, 4096))]
+        return False
 
 
 def launch_count():

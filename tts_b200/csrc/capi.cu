@@ -19,6 +19,46 @@ const char* b200tts_last_error(void) { return last_error(); }
 unsigned long long b200tts_launch_count(void) { return g_launch_count; }
 int b200tts_version(void) { return 100; }
 int b200tts_debug_tc_error(void) { return conv_tc_error_flag(); }
+void b200tts_debug_dispatch_begin(void) { dispatch_begin(); }
+int b200tts_debug_dispatch_end(int32_t* ids, int cap) { return dispatch_end(ids, cap); }
+
+struct b200tts_conv1d { ConvLayer L; b200tts_conv1d_config c; ~b200tts_conv1d() { free_conv(L); } };
+
+int b200tts_conv1d_create(const b200tts_conv1d_config* cfg, const float* weight, const float* bias, int allow_tensor_cores,
+                          b200tts_conv1d** out) {
+    if (!cfg || !weight || !out) { set_error("conv1d_create: null argument"); return 1; }
+    *out = nullptr;
+    b200tts_conv1d* h = new (std::nothrow) b200tts_conv1d();
+    if (!h) { set_error("conv1d_create: out of host memory"); return 1; }
+    h->c = *cfg;
+    int rc = cfg->transposed
+                 ? pack_conv_transpose(h->L, weight, bias, cfg->in_channels, cfg->out_channels, cfg->kernel_size,
+                                       cfg->stride, cfg->padding)
+                 : pack_conv(h->L, weight, bias, cfg->out_channels, cfg->in_channels, cfg->kernel_size, cfg->dilation,
+                             cfg->padding);
+    if (rc) { delete h; return rc; }
+    h->L.allow_tc = allow_tensor_cores != 0;
+    *out = h;
+    return 0;
+}
+void b200tts_conv1d_destroy(b200tts_conv1d* h) { delete h; }
+int b200tts_conv1d_out_len(const b200tts_conv1d* h, int T) {
+    if (!h) return 0;
+    if (h->c.transposed) return conv_transpose_out_len(h->L, T);
+    return T + 2 * h->c.padding - h->c.dilation * (h->c.kernel_size - 1);
+}
+int b200tts_conv1d_forward(const b200tts_conv1d* h, const float* x, int B, int T, float in_slope, const float* residual,
+                           float scale, int accumulate, float post_div, float* y, void* stream) {
+    if (!h) { set_error("conv1d_forward: null handle"); return 1; }
+    const int Tout = b200tts_conv1d_out_len(h, T);
+    ConvIO io;
+    io.x = x; io.x_bs = (long long)h->c.in_channels * T; io.x_cs = T; io.Tin = T; io.in_slope = in_slope;
+    io.y = y; io.y_bs = (long long)h->c.out_channels * Tout; io.y_cs = Tout; io.Tout = Tout; io.B = B;
+    if (residual) { io.res = residual; io.res_bs = io.y_bs; io.res_cs = Tout; }
+    io.scale = scale; io.post_div = post_div;
+    if (accumulate) io.flags |= EPI_ACCUM;
+    return launch_conv(h->L, io, (cudaStream_t)stream);
+}
 
 size_t b200tts_mas_workspace_bytes(int B, int Tx, int Ty) { return mas_workspace_bytes(B, Tx, Ty); }
 
@@ -127,8 +167,9 @@ int b200tts_sdp_reverse(const b200tts_sdp* h, const float* x, const float* mask,
 }
 
 int b200tts_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
-                      float* cum, int64_t* y_lengths, void* stream) {
-    return launch_durations(logw, x_mask, length_scale, B, T, w_ceil, cum, (long long*)y_lengths, (cudaStream_t)stream);
+                      float* cum, int64_t* y_lengths, const int32_t* err_flag, int64_t* meta, void* stream) {
+    return launch_durations(logw, x_mask, length_scale, B, T, w_ceil, cum, (long long*)y_lengths, err_flag,
+                            (long long*)meta, (cudaStream_t)stream);
 }
 int b200tts_expand_prior(const float* cum, const float* x_mask, const int64_t* y_lengths, const float* stats,
                          const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn,

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -31,6 +33,33 @@ const char* last_error();
             return 1;                                                                       \
         }                                                                                   \
     } while (0)
+
+// ------------------------------------------------------------------ per-device one-time initialisation
+// Function attributes (cudaFuncSetAttribute), device-side flags and the SM count belong to ONE device; the Python
+// layer picks the device per tensor, so "done once per process" would leave a second GPU of the same process
+// unconfigured.  State is keyed by cudaGetDevice() and set up under a mutex (handles may be shared across threads).
+constexpr int MAX_DEVICES = 64;
+struct DeviceOnce {
+    std::mutex mu;
+    std::atomic<bool> done[MAX_DEVICES];
+    DeviceOnce() { for (auto& d : done) d.store(false); }
+};
+// Runs f(device) the first time it is called with a given current device; returns f's status (0 = ok) or 2.
+template <class F>
+inline int device_once(DeviceOnce& o, int* dev_out, F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) {
+        set_error("device_once: cannot identify the current CUDA device");
+        return 2;
+    }
+    if (dev_out) *dev_out = dev;
+    if (o.done[dev].load(std::memory_order_acquire)) return 0;
+    std::lock_guard<std::mutex> g(o.mu);
+    if (o.done[dev].load(std::memory_order_relaxed)) return 0;
+    if (int rc = f(dev)) return rc;
+    o.done[dev].store(true, std::memory_order_release);
+    return 0;
+}
 
 // launch accounting (bench.py reports "gpu_launches" from this counter)
 extern unsigned long long g_launch_count;
@@ -100,6 +129,12 @@ int pack_conv_transpose(ConvLayer& L, const float* w, const float* bias, int Cin
 void free_conv(ConvLayer& L);
 int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t stream);
 int conv_tc_error_flag();
+// which kernel family a launch_conv call dispatched to (recorded per thread between dispatch_begin/end; tests pin it)
+enum : int { DISPATCH_FMA = 0, DISPATCH_TC1 = 1, DISPATCH_TC2 = 2, DISPATCH_TC3 = 3, DISPATCH_TC3_STAGED = 4,
+             DISPATCH_TC3_GROUPED = 5, DISPATCH_ROW1 = 6, DISPATCH_RESBLOCK = 7 };
+void dispatch_begin();
+int dispatch_end(int* ids, int cap);
+void dispatch_note(int id);
 inline int conv_transpose_out_len(const ConvLayer& L, int Tin) {
     return (Tin - 1) * L.ups - 2 * L.tr_pad + L.tr_kernel;
 }

@@ -608,16 +608,17 @@ static int launch_variant(const ConvKArgs& ka, int B, int RowsPad, cudaStream_t 
     size_t smem = (size_t)KG * (2 * CIC * a.XS + 2 * CIC * a.K * CO_T) * sizeof(float);
     if (KG > 1) smem = std::max(smem, (size_t)(KG - 1) * (CJ / 2) * TJ * (NT / KG) * sizeof(u64));
     B200_REQUIRE(smem <= 227 * 1024, "conv1d: K=%d dil=%d needs %zu B of shared memory", a.K, a.dil, smem);
-    static bool attr_done = false;
-    if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI, KG>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;   // one per template instantiation
+    if (int rc = device_once(attr_once, nullptr, [](int) -> int {
+            B200_CUDA_OK(cudaFuncSetAttribute(conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI, KG>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            return 0;
+        })) return rc;
     dim3 grid((a.Tq + T_T - 1) / T_T, RowsPad / CO_T, B);
     B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv1d: grid too large");
     conv1d_kernel<CJ, TJ, WCO, WT, CIC, EPI, KG><<<grid, NT, smem, st>>>(a);
     count_launch();
+    dispatch_note(DISPATCH_FMA);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -650,8 +651,26 @@ static int launch_cic(const ConvKArgs& a, int co_tile, int B, int RowsPad, cudaS
     return launch_tiles<16, EPI>(a, co_tile, B, RowsPad, st);
 }
 
+// ------------------------------------------------------------------ dispatch log (debug / tests)
+static thread_local std::vector<int>* t_dispatch = nullptr;
+void dispatch_begin() { delete t_dispatch; t_dispatch = new std::vector<int>(); }
+int dispatch_end(int* ids, int cap) {
+    if (!t_dispatch) return 0;
+    const int n = (int)t_dispatch->size();
+    for (int i = 0; i < n && i < cap; ++i) ids[i] = (*t_dispatch)[i];
+    delete t_dispatch;
+    t_dispatch = nullptr;
+    return n;
+}
+void dispatch_note(int id) { if (t_dispatch) t_dispatch->push_back(id); }
+
 // tcgen05 path: returns -1 when the layer / shape / epilogue is not eligible (caller falls through to the FMA kernel)
-static int* g_tc_err = nullptr;
+// Per-device state of the tcgen05 path: the pipeline-timeout flag lives in mapped pinned host memory (the kernels
+// write it with a system-scope store), so every later launch on that device reads it WITHOUT a synchronisation and
+// fails loudly instead of returning garbage audio.
+struct TcDevice { int* err = nullptr; int num_sms = 0; };
+static TcDevice g_tc_dev[MAX_DEVICES];
+static DeviceOnce g_tc_once;
 
 // launch with programmatic stream serialization: the kernel may be scheduled while its predecessor drains (the kernel
 // itself waits with griddepcontrol.wait before touching activations).  B200TTS_NO_PDL=1 restores plain launches.
@@ -671,7 +690,7 @@ static cudaError_t launch_tc3(tc3::Tc3Kernel k, int grid, size_t smem, cudaStrea
     return cudaLaunchKernelEx(&cfg, k, t);
 }
 static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
-    static int enabled = -1, v2_enabled = -1, grouped_enabled = 1, num_sms = 0;
+    static int enabled = -1, v2_enabled = -1, grouped_enabled = 1;
     if (enabled < 0) {
         const char* e3 = getenv("B200TTS_NO_TCG");
         grouped_enabled = (e3 && atoi(e3)) ? 0 : 1;
@@ -683,22 +702,26 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
     if (!enabled || !L.allow_tc || !L.w_tc || a.Tq < 128) return -1;
     if (a.act == ACT_LOGCLAMP || a.act == ACT_TANH) return -1;
     const bool needs_v3 = (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2 | EPI_GATE)) != 0;
-    static bool init_done = false;
-    if (!init_done) {
+    int dev = 0;
+    if (int rc = device_once(g_tc_once, &dev, [](int d) -> int {
         B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc2::conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         for (int g : {2, 4})
-            for (int d : {0, 1, 3, 5})
-                B200_CUDA_OK(cudaFuncSetAttribute(tc3::grouped_kernel(g, d), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B200_CUDA_OK(cudaMalloc((void**)&g_tc_err, sizeof(int)));
-        B200_CUDA_OK(cudaMemset(g_tc_err, 0, sizeof(int)));
-        int dev = 0;
-        B200_CUDA_OK(cudaGetDevice(&dev));
-        B200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        init_done = true;
-    }
+            for (int dl : {0, 1, 3, 5})
+                B200_CUDA_OK(cudaFuncSetAttribute(tc3::grouped_kernel(g, dl), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int* flag = nullptr;
+        B200_CUDA_OK(cudaHostAlloc((void**)&flag, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        *flag = 0;
+        g_tc_dev[d].err = flag;    // unified addressing: the host pointer is valid on the device
+        B200_CUDA_OK(cudaDeviceGetAttribute(&g_tc_dev[d].num_sms, cudaDevAttrMultiProcessorCount, d));
+        return 0;
+    })) return rc;
+    int* const g_tc_err = g_tc_dev[dev].err;
+    const int num_sms = g_tc_dev[dev].num_sms;
+    B200_REQUIRE(*reinterpret_cast<volatile int*>(g_tc_err) == 0,
+                 "tcgen05 conv: an earlier launch on device %d hit a pipeline timeout (its output is invalid)", dev);
     const int rows_pad = (tc::TT + (L.K - 1) * L.dil + 7) / 8 * 8;
     // ---- persistent kernel (needs 16-byte aligned activation rows for its cp.async staging; no input mask)
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) && (a.x_cs % 4 == 0) && (a.x_bs % 4 == 0);
@@ -727,6 +750,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             const int grid = (int)(tiles < num_sms ? tiles : num_sms);
             B200_CUDA_OK(launch_tc3(tc3::grouped_kernel(G, L.dil), grid, tc3::smem_bytes3(rp, rp + 4), st, t));
             count_launch();
+            dispatch_note(DISPATCH_TC3_GROUPED);
             B200_CUDA_OK(cudaGetLastError());
             return 0;
         }
@@ -766,6 +790,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         const int grid = (int)(tiles < num_sms ? tiles : num_sms);
         B200_CUDA_OK(launch_tc3(t.stage ? tc3::conv1d_tc3s_kernel : tc3::conv1d_tc3_kernel, grid, smem3, st, t));
         count_launch();
+        dispatch_note(t.stage ? DISPATCH_TC3_STAGED : DISPATCH_TC3);
         B200_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -789,6 +814,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         const int grid = (int)(tiles < num_sms ? tiles : num_sms);
         tc2::conv1d_tc2_kernel<<<grid, tc2::NTHREADS2, smem2, st>>>(t);
         count_launch();
+        dispatch_note(DISPATCH_TC2);
         B200_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -813,15 +839,15 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
     if (grid.y > 65535 || grid.z > 65535) return -1;
     tc::conv1d_tc_kernel<<<grid, tc::NTHREADS, smem, st>>>(t);
     count_launch();
+    dispatch_note(DISPATCH_TC1);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int conv_tc_error_flag() {   // 1 if any tcgen05 launch hit a pipeline timeout (debug aid; synchronises)
-    if (!g_tc_err) return 0;
-    int h = 0;
-    cudaMemcpy(&h, g_tc_err, sizeof(int), cudaMemcpyDeviceToHost);
-    return h;
+int conv_tc_error_flag() {   // 1 if any tcgen05 launch (on any device) hit a pipeline timeout; call after a sync
+    for (int d = 0; d < MAX_DEVICES; ++d)
+        if (g_tc_dev[d].err && *reinterpret_cast<volatile int*>(g_tc_dev[d].err)) return 1;
+    return 0;
 }
 
 int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
@@ -861,6 +887,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
                                                                                  L.co_tile, L.bias, a.in_slope, a.act, a.y,
                                                                                  a.y_bs);
                 count_launch();
+                dispatch_note(DISPATCH_ROW1);
                 B200_CUDA_OK(cudaGetLastError());
                 return 0;
             }

@@ -75,7 +75,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
         if (ok) return true;
         if (sleep_ns) __nanosleep(sleep_ns);
     }
-    if (err) atomicExch(err, 1);
+    if (err) { *reinterpret_cast<volatile int*>(err) = 1; __threadfence_system(); }   // mapped host flag (conv1d.cu)
     return false;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

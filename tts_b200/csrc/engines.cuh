@@ -127,7 +127,7 @@ struct Stft {
 
 // durations -> path -> expanded prior (path.cu)
 int launch_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
-                     float* cum, long long* y_lengths, cudaStream_t st);
+                     float* cum, long long* y_lengths, const int* err_flag, long long* meta, cudaStream_t st);
 int launch_expand_prior(const float* cum, const float* x_mask, const long long* y_lengths, const float* stats,
                         const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn, float* m_p,
                         float* logs_p, float* z_p, float* y_mask, cudaStream_t st);

@@ -389,18 +389,18 @@ int mas_forward(const float* value, const float* mask, const int* t_x, const int
     B200_REQUIRE(B >= 0 && Tx >= 0 && Ty >= 0, "mas: negative size");
     if (B == 0 || Tx == 0 || Ty == 0) return 0;
     B200_REQUIRE(value && t_x && t_y && path, "mas: null pointer");
-    static bool attr2_done = false;
+    static DeviceOnce attr2_once, attr_once;
     if (Tx <= MAS_NT) {     // lean kernel
         bool dsm = mas2_smem(Tx, Ty, mask != nullptr, true) <= 72 * 1024;
         const size_t smem2 = mas2_smem(Tx, Ty, mask != nullptr, dsm);
         if (smem2 <= 200 * 1024 && (dsm || (ws && ws_bytes >= mas_workspace_bytes(B, Tx, Ty)))) {
-            if (!attr2_done) {
-                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr2_done = true;
-            }
+            if (int rc = device_once(attr2_once, nullptr, [](int) -> int {
+                    B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    return 0;
+                })) return rc;
             MasArgs a2;
             a2.value = value; a2.mask = mask; a2.t_x = t_x; a2.t_y = t_y;
             a2.B = B; a2.Tx = Tx; a2.Ty = Ty; a2.YT = MAS2_YT; a2.W = (Tx + 31) / 32;
@@ -418,11 +418,10 @@ int mas_forward(const float* value, const float* mask, const int* t_x, const int
     MasPlan p = mas_plan(Tx, Ty, mask != nullptr);
     B200_REQUIRE(p.ok, "mas: Tx=%d Ty=%d does not fit the shared-memory plan", Tx, Ty);
     B200_REQUIRE(p.dirs_in_smem || (ws && ws_bytes >= mas_workspace_bytes(B, Tx, Ty)), "mas: workspace too small");
-    static bool attr_done = false;
-    if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    if (int rc = device_once(attr_once, nullptr, [](int) -> int {
+            B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            return 0;
+        })) return rc;
     MasArgs a;
     a.value = value; a.mask = mask; a.t_x = t_x; a.t_y = t_y;
     a.B = B; a.Tx = Tx; a.Ty = Ty; a.YT = p.YT; a.W = (Tx + 31) / 32;

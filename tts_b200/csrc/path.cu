@@ -10,30 +10,48 @@ namespace b200tts {
 
 namespace {
 
-// one warp per utterance: inclusive scan of integral-valued fp32 durations (exact below 2^24)
+// one warp per utterance (one CTA, warps stride over the batch): inclusive scan of integral-valued fp32 durations
+// (exact below 2^24).  The same CTA reduces max(y_lengths) and forwards the duration predictor's error flag into
+// `meta` = {max y_length, flag}, so the caller's one host read fetches both (no second synchronisation).
 __global__ void durations_kernel(const float* logw, const float* x_mask, float length_scale, float* w_ceil,
-                                 float* cum, long long* y_lengths, int T) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    float carry = 0.f;
-    for (int t0 = 0; t0 < T; t0 += 32) {
-        const int t = t0 + lane;
-        float wc = 0.f;
-        if (t < T) {
-            const float w = __fmul_rn(__fmul_rn(expf(logw[(size_t)b * T + t]), x_mask[(size_t)b * T + t]), length_scale);
-            wc = ceilf(w);
-            w_ceil[(size_t)b * T + t] = wc;
-        }
-        float s = wc;
+                                 float* cum, long long* y_lengths, int B, int T, const int* err_flag, long long* meta) {
+    __shared__ long long wmax[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    long long mymax = 0;
+    for (int b = warp; b < B; b += nwarps) {
+        float carry = 0.f;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            float wc = 0.f;
+            if (t < T) {
+                const float w = __fmul_rn(__fmul_rn(expf(logw[(size_t)b * T + t]), x_mask[(size_t)b * T + t]), length_scale);
+                wc = ceilf(w);
+                w_ceil[(size_t)b * T + t] = wc;
+            }
+            float s = wc;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float n = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += n;
+            for (int o = 1; o < 32; o <<= 1) {
+                const float n = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += n;
+            }
+            s += carry;
+            if (t < T) cum[(size_t)b * T + t] = s;
+            carry = __shfl_sync(0xffffffffu, s, 31);
         }
-        s += carry;
-        if (t < T) cum[(size_t)b * T + t] = s;
-        carry = __shfl_sync(0xffffffffu, s, 31);
+        const long long yl = (long long)fmaxf(carry, 1.f);
+        if (lane == 0) y_lengths[b] = yl;
+        mymax = yl > mymax ? yl : mymax;
     }
-    if (lane == 0) y_lengths[b] = (long long)fmaxf(carry, 1.f);
+    if (meta) {
+        if (lane == 0) wmax[warp] = mymax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long m = 0;
+            for (int i = 0; i < nwarps; ++i) m = wmax[i] > m ? wmax[i] : m;
+            meta[0] = m;
+            meta[1] = err_flag ? (long long)err_flag[0] : 0;
+        }
+    }
 }
 
 // one thread per decoder frame: token index by binary search over the cumulative durations
@@ -73,10 +91,11 @@ __global__ void expand_prior_kernel(const float* cum, const float* x_mask, const
 }  // namespace
 
 int launch_durations(const float* logw, const float* x_mask, float length_scale, int B, int T, float* w_ceil,
-                     float* cum, long long* y_lengths, cudaStream_t st) {
+                     float* cum, long long* y_lengths, const int* err_flag, long long* meta, cudaStream_t st) {
     B200_REQUIRE(logw && x_mask && w_ceil && cum && y_lengths, "durations: null pointer");
     if (B == 0) return 0;
-    durations_kernel<<<B, 32, 0, st>>>(logw, x_mask, length_scale, w_ceil, cum, y_lengths, T);
+    durations_kernel<<<1, 32 * (B < 32 ? B : 32), 0, st>>>(logw, x_mask, length_scale, w_ceil, cum, y_lengths, B, T,
+                                                          err_flag, meta);
     count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -118,11 +118,11 @@ int Stft::magnitude(const float* wav, int B, int T, int pad1, int pad2, int mode
                  "stft_magnitude: n_frames=%d exceeds the padded signal", n_frames);
     const int F = n_fft / 2 + 1;
     const size_t smem = sizeof(float) * (2 * (size_t)n_fft + (size_t)STFT_FR * F);
-    static bool attr_done = false;
-    if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    if (int rc = device_once(attr_once, nullptr, [](int) -> int {
+            B200_CUDA_OK(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            return 0;
+        })) return rc;
     dim3 grid((n_frames + STFT_FR - 1) / STFT_FR, B);
     stft_mag_kernel<<<grid, STFT_NT, smem, st>>>(wav, window, reinterpret_cast<const float2*>(twiddle), spec, T, n_fft,
                                                  log2n, hop, pad1, pad2, n_frames, mode, power);

@@ -307,11 +307,11 @@ int TextEncoder::forward(const long long* tokens, const long long* lengths, cons
     const size_t att_smem = sizeof(float) * ((size_t)ATT_Q * d + (size_t)ATT_Q * Tp + (size_t)(ATT_KT + 1) * (d + 1) +
                                              (size_t)2 * nrel * d);
     B200_REQUIRE(att_smem <= 200 * 1024, "text_encoder_forward: T=%d too long for the attention kernel", T);
-    static bool attr_done = false;
-    if (!attr_done) {
-        B200_CUDA_OK(cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    if (int rc0 = device_once(attr_once, nullptr, [](int) -> int {
+            B200_CUDA_OK(cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            return 0;
+        })) return rc0;
     int rc;
     for (int l = 0; l < c.num_layers; ++l) {
         const Layer& L = *layers[l];

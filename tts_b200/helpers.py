@@ -32,10 +32,11 @@ def maximum_path_lengths(value, t_x, t_y, mask=None, out_dtype=None):
     t_x = t_x.to(device=value.device, dtype=torch.int32).contiguous()
     t_y = t_y.to(device=value.device, dtype=torch.int32).contiguous()
     L = _lib.lib()
-    nbytes = L.b200tts_mas_workspace_bytes(b, tx, ty)
-    ws = _lib.workspace(value.device, nbytes, "mas")
-    rc = L.b200tts_mas(_lib.ptr(value), _lib.ptr(mask), _lib.ptr(t_x), _lib.ptr(t_y), b, tx, ty, _lib.ptr(path),
-                       1 if f32 else 0, _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr(value.device))
+    with torch.cuda.device(value.device):
+        nbytes = L.b200tts_mas_workspace_bytes(b, tx, ty)
+        ws = _lib.workspace(value.device, nbytes, "mas")
+        rc = L.b200tts_mas(_lib.ptr(value), _lib.ptr(mask), _lib.ptr(t_x), _lib.ptr(t_y), b, tx, ty, _lib.ptr(path),
+                           1 if f32 else 0, _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr(value.device))
     _lib.check(rc, "mas")
     return path
 

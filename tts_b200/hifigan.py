@@ -100,6 +100,10 @@ class HifiganGenerator(nn.Module):
             remove_parametrizations(self.conv_post, "weight")
         self._handle = None
         self._handle_device = None
+        # a parent's load_state_dict never calls a child's load_state_dict() override (it recurses through
+        # _load_from_state_dict), so the packed handle is dropped from a pre-hook: Vits.load_checkpoint twice in a row
+        # must not keep the first checkpoint's decoder weights
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self._drop_handle())
 
     # ------------------------------------------------------------------ engine handle
     def _drop_handle(self):
@@ -116,10 +120,6 @@ class HifiganGenerator(nn.Module):
     def _apply(self, fn, *a, **kw):
         self._drop_handle()
         return super()._apply(fn, *a, **kw)
-
-    def load_state_dict(self, *a, **kw):
-        self._drop_handle()
-        return super().load_state_dict(*a, **kw)
 
     def repack(self):
         """Re-read the parameters (call after modifying weights in place)."""

@@ -164,16 +164,33 @@ class ResidualCouplingBlocks(EngineModule):
             tensors += _wb(f.pre) + f.enc.ordered_weights() + _wb(f.post)
         return self._make("b200tts_flow_create_forward" if forward_direction else "b200tts_flow_create", cfg, tensors)
 
-    def _drop_handle(self):
-        super()._drop_handle()
+    def _drop_forward_handle(self):
         h = self.__dict__.get("_handle_fwd", None)
         if h is not None:
             _lib.lib().b200tts_flow_destroy(h)
         self._handle_fwd = None
 
+    def _drop_handle(self):
+        """Both directions (weights changed: _apply / load_state_dict hook / repack / __del__)."""
+        self._drop_reverse_handle()
+        self._drop_forward_handle()
+
+    def _drop_reverse_handle(self):
+        EngineModule._drop_handle(self)
+
+    def handle(self, device):
+        # the two directions own separate handles: (re)creating one must not destroy the other (voice conversion
+        # calls forward then reverse on every utterance)
+        if self._handle is None or self._handle_device != device:
+            self._drop_reverse_handle()
+            with torch.cuda.device(device):
+                self._handle = self._create(device)
+            self._handle_device = device
+        return self._handle
+
     def _forward_handle(self, device):
         if self.__dict__.get("_handle_fwd", None) is None or self._handle_fwd_device != device:
-            self._drop_handle()
+            self._drop_forward_handle()
             with torch.cuda.device(device):
                 self._handle_fwd = self._create(device, forward_direction=True)
             self._handle_fwd_device = device
@@ -578,8 +595,9 @@ class StochasticDurationPredictor(EngineModule):
         return logw
 
 
-def durations_to_path(logw, x_mask, length_scale):
-    """Stage 1 of vits.py:1140-1146 on the device: returns (w_ceil [B,1,T], cum [B,T], y_lengths int64 [B])."""
+def durations_to_path(logw, x_mask, length_scale, err_flag=None):
+    """Stage 1 of vits.py:1140-1146 on the device: returns (w_ceil [B,1,T], cum [B,T], y_lengths int64 [B],
+    meta int64 [2] = {max(y_lengths), err_flag}) -- one D2H read of ``meta`` is the path's only host sync."""
     dev = logw.device
     b, _, t = logw.shape
     logw = logw.to(torch.float32).contiguous()
@@ -587,11 +605,13 @@ def durations_to_path(logw, x_mask, length_scale):
     w_ceil = torch.empty((b, 1, t), dtype=torch.float32, device=dev)
     cum = torch.empty((b, t), dtype=torch.float32, device=dev)
     y_lengths = torch.empty((b,), dtype=torch.int64, device=dev)
+    meta = torch.empty((2,), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.lib().b200tts_durations(_lib.ptr(logw), _lib.ptr(mask), ctypes.c_float(length_scale), b, t,
-                                          _lib.ptr(w_ceil), _lib.ptr(cum), _lib.ptr(y_lengths), _lib.stream_ptr(dev))
+                                          _lib.ptr(w_ceil), _lib.ptr(cum), _lib.ptr(y_lengths), _lib.ptr(err_flag),
+                                          _lib.ptr(meta), _lib.stream_ptr(dev))
     _lib.check(rc, "durations")
-    return w_ceil, cum, y_lengths
+    return w_ceil, cum, y_lengths, meta
 
 
 def expand_prior(cum, x_mask, y_lengths, stats, noise, noise_scale, t_dec, want_attn=True):

@@ -307,26 +307,32 @@ class Vits(nn.Module):
         with _Stage(self, "text_encoder"):
             h, stats, x_mask = self.text_encoder.forward_stats(x, x_lengths, lang_emb=lang_emb)
         with _Stage(self, "duration_predictor"):
-            logw = None
+            logw, meta = None, None
             if durations is not None:
                 w = durations.to(device=x.device, dtype=torch.float32).reshape(1, 1, -1)
                 w_ceil = torch.ceil(w)
                 cum = torch.cumsum(w_ceil.reshape(1, -1), dim=1)
                 y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
             else:
+                flag = None
                 if a.use_sdp:
                     logw = self.duration_predictor(h, x_mask, g=g if a.condition_dp_on_speaker else None,
                                                    reverse=True, noise_scale=self.inference_noise_scale_dp,
                                                    lang_emb=lang_emb, noise=sdp_noise)
+                    # consumed here: a stale flag must not be re-read by a later call that supplies durations
+                    flag, self.duration_predictor.last_error_flag = self.duration_predictor.last_error_flag, None
                 else:
                     logw = self.duration_predictor(h, x_mask, g=g if a.condition_dp_on_speaker else None,
                                                    lang_emb=lang_emb)
-                w_ceil, cum, y_lengths = durations_to_path(logw, x_mask, float(self.length_scale))
-        # the one host sync of the path: T_dec = max(y_lengths) (sequence_mask(y_lengths, None), helpers.py:53-54)
-        t_dec = int(y_lengths.max().item())
-        flag = getattr(self.duration_predictor, "last_error_flag", None)
-        if flag is not None and int(flag.item()) != 0:
-            raise AssertionError("spline discriminant < 0 (TTS/tts/layers/vits/transforms.py:168)")
+                w_ceil, cum, y_lengths, meta = durations_to_path(logw, x_mask, float(self.length_scale), err_flag=flag)
+        # the one host sync of the path: T_dec = max(y_lengths) (sequence_mask(y_lengths, None), helpers.py:53-54),
+        # read together with the spline error flag in a single 16-byte D2H copy
+        if meta is not None:
+            t_dec, bad = (int(v) for v in meta.tolist())
+            if bad != 0:
+                raise AssertionError("spline discriminant < 0 (TTS/tts/layers/vits/transforms.py:168)")
+        else:
+            t_dec = int(y_lengths.max().item())
         c = a.hidden_channels
         if prior_noise is None:
             noise = torch.randn((x.shape[0], c, t_dec), dtype=torch.float32, device=x.device)
@@ -338,6 +344,7 @@ class Vits(nn.Module):
             attn, m_p, logs_p, z_p, y_mask = expand_prior(cum, x_mask, y_lengths, stats, noise,
                                                           float(self.inference_noise_scale), t_dec,
                                                           want_attn=return_alignments)
+        frame_lengths = y_lengths            # valid decoder frames per utterance at the decoder's input rate
         with _Stage(self, "flow"):
             z = self.flow(z_p, y_mask, g=g, reverse=True)
             if a.encoder_sample_rate and a.interpolate_z:   # upsampling_z, vits.py:944-959
@@ -348,13 +355,19 @@ class Vits(nn.Module):
                 if y_mask.shape[-1] != z.shape[-1]:
                     raise ValueError("tts_b200.Vits: sample_rate / encoder_sample_rate must scale the frame count to an "
                                      "integer (the reference's z * y_mask fails the same way, vits.py:1160)")
+                frame_lengths = torch.ceil(len_up).long()    # frames t with t < y_lengths * f, as the rebuilt mask counts
             zin = z * y_mask
             if self.max_inference_len is not None:
                 zin = zin[:, :, : self.max_inference_len]
+                frame_lengths = torch.clamp_max(frame_lengths, int(self.max_inference_len))
         with _Stage(self, "waveform_decoder"):
             o = self.waveform_decoder(zin, g=g)
+        hop = o.shape[-1] // max(zin.shape[-1], 1)      # prod(upsample_rates_decoder)
+        # the reference's eight keys (vits.py:1163-1172) plus: y_lengths (frames at the text-side rate), logw, and
+        # wav_lengths = valid output samples per utterance (after latent upsampling / max_inference_len cropping)
         return {"model_outputs": o, "alignments": attn, "durations": w_ceil, "z": z, "z_p": z_p, "m_p": m_p,
-                "logs_p": logs_p, "y_mask": y_mask, "y_lengths": y_lengths, "logw": logw}
+                "logs_p": logs_p, "y_mask": y_mask, "y_lengths": y_lengths, "logw": logw,
+                "wav_lengths": frame_lengths * hop}
 
     # ------------------------------------------------------------------ voice conversion (vits.py:1175-1232)
     @torch.no_grad()
@@ -411,6 +424,7 @@ class Vits(nn.Module):
             n_new = self.emb_g.weight.shape[0] - model["emb_g.weight"].shape[0]
             model["emb_g.weight"] = torch.cat([model["emb_g.weight"], torch.randn(n_new, model["emb_g.weight"].shape[1])], 0)
         self.load_state_dict(model, strict=strict)
+        self.repack()      # packed device handles are rebuilt from the new weights on the next call
         if eval:
             self.eval()
             assert not self.training
