@@ -55,6 +55,8 @@ struct Args {
     int kstep;       // B and A start advanced by kstep * 32 bytes inside the swizzle row
     int use_base_off;
     int vary;        // rate mode: rotate through `vary` different B start rows (like taps)
+    int vstep;       // rows between those starts
+    int avary;       // rate mode: rotate through `avary` different (aligned) A tiles, 4 KB apart (like per-tap weight blocks)
     const float* A;  // [128][KW]   (KW = floats per row of the layout: 8, 16, 32; none: 8)
     const float* B;  // [ROWS_B][KW]
     float* D;        // [128][N]
@@ -127,14 +129,15 @@ __global__ void __launch_bounds__(192, 1) k_mma(const Args a) {
         }
         long long t0 = clock64();
         for (int i = 0; i < a.nmma; ++i) {
-            const int sh = a.shift_rows + (a.vary > 1 ? (i % a.vary) * 3 : 0);
+            const int sh = a.shift_rows + (a.vary > 1 ? (i % a.vary) * a.vstep : 0);
+            const uint64_t aoff = a.avary > 1 ? (uint64_t)(((i % a.avary) * 4096) >> 4) : 0;   // next 128-row A tile
             uint64_t bdesc;
             if (a.layout == 0) bdesc = bdesc0 + (uint64_t)sh;     // 16-byte rows: +1 per row in the address field
             else {
                 const uint32_t sb = bbase + sh * rowb + a.kstep * 32;
                 bdesc = make_desc(sb, 16, 8 * SW, a.layout, a.use_base_off ? ((sb >> 7) & 7) : 0);
             }
-            mma_tf32(tmem, adesc, bdesc, idesc, i == 0 ? 0u : 1u);
+            mma_tf32(tmem, adesc + aoff, bdesc, idesc, i == 0 ? 0u : 1u);
         }
         mma_commit(smem_u32(bar));
         mbar_wait(smem_u32(bar), 0);
@@ -178,12 +181,26 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dcyc, sizeof(long long) * sms));
     // ------------------------------------------------------------ (1) rate
     printf("# rate: cycles per tcgen05.mma kind::tf32 M=128, K=8 (all %d SMs issuing, nmma=4096)\n", sms);
+    struct Case { int shift, vary, vstep, avary; const char* what; };
+    const Case cases[] = {
+        {0, 1, 0, 1, "fixed descriptors, aligned"},
+        {3, 1, 0, 1, "fixed descriptors, B start 3 rows off an 8-row group"},
+        {4, 1, 0, 1, "fixed descriptors, B start 4 rows off"},
+        {0, 4, 8, 1, "B rotates over 4 starts, 8 rows apart (aligned)"},
+        {0, 4, 3, 1, "B rotates over 4 starts, 3 rows apart (the conv tap pattern, dil 3)"},
+        {0, 8, 1, 1, "B rotates over 8 starts, 1 row apart (dil 1)"},
+        {0, 4, 4, 1, "B rotates over 4 starts, 4 rows apart"},
+        {0, 1, 0, 4, "A rotates over 4 aligned tiles, B fixed aligned"},
+        {0, 4, 3, 4, "A rotates (aligned), B rotates 3 rows apart"},
+    };
     for (int layout : {0, 6, 4, 2})
-        for (int N : {64, 128, 256})
-            for (int vary : {1, 4}) {
+        for (int N : {128, 256})
+            for (const Case& cs : cases) {
                 Args a; memset(&a, 0, sizeof(a));
-                a.mode = 0; a.layout = layout; a.N = N; a.nmma = 4096; a.vary = vary; a.rows_b = 320; a.cyc = dcyc;
-                a.use_base_off = 1;
+                a.mode = 0; a.layout = layout; a.N = N; a.nmma = 4096; a.vary = cs.vary; a.vstep = cs.vstep; a.avary = cs.avary;
+                a.shift_rows = cs.shift; a.rows_b = 320; a.cyc = dcyc;
+                a.use_base_off = 0;
+                if (layout != 0 && layout != 6 && cs.avary > 1) continue;   // wide-row A tiles do not fit the 32 KB A region 4x
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
                 k_mma<<<sms, 192, SMEM>>>(a);   // warm-up
@@ -197,9 +214,8 @@ int main(int argc, char** argv) {
                 CK(cudaMemcpy(h.data(), dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
                 double avg = 0; for (auto v : h) avg += (double)v; avg /= sms;
                 const double cpm = avg / a.nmma;
-                const double flops = 2.0 * 128 * N * 8 * a.nmma * sms;
-                printf("layout %-5s N %3d taps %d : %7.1f cyc/MMA  -> %7.1f dense TF32 TFLOP/s by device clock at %0.f MHz, %7.1f by event time (incl. fill)\n",
-                       lname(layout), N, vary, cpm, 2.0 * 128 * N * 8 / cpm * sms * (khz * 1e3) / 1e12, khz / 1000.0, flops / (ms * 1e-3) / 1e12);
+                printf("layout %-5s N %3d : %7.1f cyc/MMA -> %7.1f dense TF32 TFLOP/s at %.0f MHz | %s\n", lname(layout), N, cpm,
+                       2.0 * 128 * N * 8 / cpm * sms * (khz * 1e3) / 1e12, khz / 1000.0, cs.what);
             }
     // ------------------------------------------------------------ (2) shift probe
     printf("# shift probe: D = A * B[shift:]^T, max |err| vs host (tf32-exact inputs)\n");

@@ -88,7 +88,9 @@ size_t Hifigan::workspace_bytes(int B, int T) const {
     stage_dims(T, C, L);
     size_t mx = 0;
     for (size_t s = 0; s < C.size(); ++s) mx = std::max(mx, (size_t)C[s] * (size_t)L[s]);
-    size_t tot = arena_bytes((size_t)B * c.upsample_initial_channel * T);
+    const size_t Tp = (size_t)(T + 3) / 4 * 4;    // 16-byte aligned row pitch for the stage-0 tensors
+    size_t tot = arena_bytes((size_t)B * c.upsample_initial_channel * Tp);
+    tot += arena_bytes((size_t)B * c.in_channels * Tp);
     tot += 4 * arena_bytes((size_t)B * mx);
     tot += arena_bytes((size_t)B * cond.RowsPad + 64);
     return tot;
@@ -113,13 +115,26 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
     for (size_t s = 0; s < C.size(); ++s) mx = std::max(mx, (size_t)C[s] * (size_t)L[s]);
     Arena ar(ws, ws_bytes);
     const int C0 = c.upsample_initial_channel;
-    float* P = ar.f32((size_t)B * C0 * T);
+    // The tcgen05 kernels stage activation rows with 16-byte cp.async: rows must start 16-byte aligned.  T (decoder frames)
+    // is arbitrary, so the stage-0 tensors use a row pitch rounded up to 4 floats and an unaligned input is re-pitched
+    // once (B x Cin x T floats, tiny) -- otherwise conv_pre / ups[0] would silently take the FP32-FMA kernel for 3 of 4 T.
+    const int Tp = (T + 3) / 4 * 4;
+    float* P = ar.f32((size_t)B * C0 * Tp);
+    float* Xp = ar.f32((size_t)B * c.in_channels * Tp);
     float* U = ar.f32((size_t)B * mx);
     float* T1 = ar.f32((size_t)B * mx);
     float* R = ar.f32((size_t)B * mx);
     float* OUT = ar.f32((size_t)B * mx);
     float* condv = ar.f32((size_t)B * cond.RowsPad + 64);
-    B200_REQUIRE(P && U && T1 && R && OUT && condv, "hifigan_forward: arena exhausted");
+    B200_REQUIRE(P && Xp && U && T1 && R && OUT && condv, "hifigan_forward: arena exhausted");
+    const float* xin0 = x;
+    int x_pitch = T;
+    if (Tp != T || (reinterpret_cast<uintptr_t>(x) & 15) != 0) {
+        B200_CUDA_OK(cudaMemcpy2DAsync(Xp, (size_t)Tp * sizeof(float), x, (size_t)T * sizeof(float), (size_t)T * sizeof(float),
+                                       (size_t)B * c.in_channels, cudaMemcpyDeviceToDevice, st));
+        xin0 = Xp;
+        x_pitch = Tp;
+    }
     int rc;
     const bool has_cond = c.cond_channels > 0 && g != nullptr;
     if (has_cond) {  // cond_layer(g): [B, cond, 1] -> [B, C0]
@@ -130,20 +145,20 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
     }
     {  // conv_pre (+ cond broadcast over T)
         ConvIO io;
-        io.x = x; io.x_bs = (long long)c.in_channels * T; io.x_cs = T; io.Tin = T;
-        io.y = P; io.y_bs = (long long)C0 * T; io.y_cs = T; io.Tout = T; io.B = B;
+        io.x = xin0; io.x_bs = (long long)c.in_channels * x_pitch; io.x_cs = x_pitch; io.Tin = T;
+        io.y = P; io.y_bs = (long long)C0 * Tp; io.y_cs = Tp; io.Tout = T; io.B = B;
         if (has_cond) { io.cond = condv; io.cond_bs = cond.RowsPad; }
         if ((rc = launch_conv(conv_pre, io, st))) return rc;
     }
     const float* cur = P;
-    int curC = C0, curL = T;
+    int curC = C0, curL = T, curPitch = Tp;
     const bool type1 = c.resblock_type == 1;
     for (int s = 0; s < c.num_upsamples; ++s) {
         const int Cs = C[s], Ls = L[s];
         const long long bs = (long long)Cs * Ls;
         {  // o = ups(leaky_relu(o, 0.1))
             ConvIO io;
-            io.x = cur; io.x_bs = (long long)curC * curL; io.x_cs = curL; io.Tin = curL; io.in_slope = 0.1f;
+            io.x = cur; io.x_bs = (long long)curC * curPitch; io.x_cs = curPitch; io.Tin = curL; io.in_slope = 0.1f;
             io.y = U; io.y_bs = bs; io.y_cs = Ls; io.Tout = Ls; io.B = B;
             if ((rc = launch_conv(ups[s], io, st))) return rc;
         }
@@ -184,12 +199,13 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
         cur = OUT;
         curC = Cs;
         curL = Ls;
+        curPitch = Ls;
         // the next stage's ups reads OUT and writes U; OUT is only rewritten by later launches
         // on the same stream, after that read has completed.
     }
     {  // tanh(conv_post(leaky_relu(o)))  -- default slope 0.01 (hifigan_generator.py:262)
         ConvIO io;
-        io.x = cur; io.x_bs = (long long)curC * curL; io.x_cs = curL; io.Tin = curL; io.in_slope = 0.01f;
+        io.x = cur; io.x_bs = (long long)curC * curPitch; io.x_cs = curPitch; io.Tin = curL; io.in_slope = 0.01f;
         io.y = wav; io.y_bs = (long long)c.out_channels * curL; io.y_cs = curL; io.Tout = curL; io.B = B;
         io.act = ACT_TANH;
         if ((rc = launch_conv(conv_post, io, st))) return rc;
