@@ -114,6 +114,39 @@ int b200tts_hifigan_out_len(const b200tts_hifigan* h, int T);
 int b200tts_hifigan_forward(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same as b200tts_hifigan_forward; additionally conv_post's store folds max|wav| over everything it writes into
+ * *peak_bits (atomicMax on the float's bit pattern; the caller zeroes the word first, several calls may share it):
+ * the first half of save_wav's peak normalisation, TTS/utils/audio/numpy_transforms.py:439, without another pass. */
+int b200tts_hifigan_forward_peak(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
+                                 uint32_t* peak_bits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- hand-off around a standalone vocoder ---------------------------------------------------------
+ * b200tts_vocoder_input replaces, in one pass on the device, what Synthesizer.tts does on the host between the TTS
+ * model and the vocoder (TTS/utils/synthesizer.py:412-429):
+ *   tts_ap.denormalize (TTS/utils/audio/processor.py:303-337)  ->  vocoder_ap.normalize (:259-301)
+ *   -> interpolate_vocoder_input (TTS/vocoder/utils/generic_utils.py:11-29; bilinear, align_corners=False,
+ *      recompute_scale_factor=True, scale [1, scale_factor])   -> replicate padding of HifiganGenerator.inference
+ *      (TTS/vocoder/models/hifigan_generator.py:281)
+ * x is addressed as x[b*x_batch_stride + c*x_channel_stride + t*x_time_stride] (the TTS model's [B,T,C] output or a
+ * [B,C,T] spectrogram alike); y is [B, C, y_pitch] with b200tts_vocoder_input_len(T, scale_factor, padding) valid
+ * columns per row (give y_pitch a multiple of 4 for the tensor-core kernels).  scaler_mean / scaler_scale: DEVICE
+ * pointers to the [C] statistics of a mean-var AudioProcessor (stats_path), NULL otherwise.
+ * b200tts_absmax / b200tts_to_int16: save_wav's `wav * (32767 / max(0.01, max|wav|))` -> int16
+ * (TTS/utils/audio/numpy_transforms.py:439-441); *peak_bits as above.
+ */
+typedef struct {
+    int signal_norm, symmetric_norm, clip_norm;
+    float max_norm, min_level_db, ref_level_db;
+    const float* scaler_mean;
+    const float* scaler_scale;
+} b200tts_audio_norm;
+int b200tts_vocoder_input_len(int T, float scale_factor, int padding);
+int b200tts_vocoder_input(const float* x, long long x_batch_stride, int x_channel_stride, int x_time_stride, int B, int C,
+                          int T, const b200tts_audio_norm* denormalize, const b200tts_audio_norm* normalize,
+                          float scale_factor, int padding, float* y, int y_pitch, void* stream);
+int b200tts_absmax(const float* x, long long n, uint32_t* peak_bits, void* stream);
+int b200tts_to_int16(const float* x, long long n, const uint32_t* peak_bits, int16_t* out, void* stream);
+
 /* ---- residual-coupling flow, reverse direction ------------------------------------------------
  * Replaces ResidualCouplingBlocks.forward(reverse=True), TTS/tts/layers/vits/networks.py:214-232
  * (blocks :138-166, WaveNet TTS/tts/layers/generic/wavenet.py:94-115) as called at vits.py:1156.

@@ -609,3 +609,73 @@ def torch_stft_call(x, n_fft, hop_length, win_length, *, pad_wav=False, power=No
     if do_amp_to_db:
         s = torch.log(torch.clamp(s, min=1e-5) * spec_gain)
     return s
+
+
+# --------------------------------------------------------------------------- vocoder hand-off (Synthesizer.tts)
+def audio_normalize(S, *, signal_norm=True, symmetric_norm=True, max_norm=4.0, clip_norm=True, min_level_db=-100.0,
+                    ref_level_db=20.0, mel_mean=None, mel_std=None):
+    """AudioProcessor.normalize, utils/audio/processor.py:259-301 (S float32 numpy [C,T]; the mean-var branch is
+    StandardScaler.transform with the given per-channel statistics)."""
+    S = np.array(S, dtype=np.float32, copy=True)
+    if not signal_norm:
+        return S
+    if mel_mean is not None:
+        return ((S.T - np.asarray(mel_mean, dtype=np.float32)) / np.asarray(mel_std, dtype=np.float32)).T
+    S -= np.float32(ref_level_db)
+    S_norm = (S - np.float32(min_level_db)) / np.float32(-min_level_db)
+    if symmetric_norm:
+        S_norm = (np.float32(2 * max_norm) * S_norm) - np.float32(max_norm)
+        if clip_norm:
+            S_norm = np.clip(S_norm, -max_norm, max_norm)
+        return S_norm.astype(np.float32)
+    S_norm = np.float32(max_norm) * S_norm
+    if clip_norm:
+        S_norm = np.clip(S_norm, 0, max_norm)
+    return S_norm.astype(np.float32)
+
+
+def audio_denormalize(S, *, signal_norm=True, symmetric_norm=True, max_norm=4.0, clip_norm=True, min_level_db=-100.0,
+                      ref_level_db=20.0, mel_mean=None, mel_std=None):
+    """AudioProcessor.denormalize, utils/audio/processor.py:303-337."""
+    S = np.array(S, dtype=np.float32, copy=True)
+    if not signal_norm:
+        return S
+    if mel_mean is not None:
+        return (S.T * np.asarray(mel_std, dtype=np.float32) + np.asarray(mel_mean, dtype=np.float32)).T
+    if symmetric_norm:
+        if clip_norm:
+            S = np.clip(S, -max_norm, max_norm)
+        S = ((S + np.float32(max_norm)) * np.float32(-min_level_db) / np.float32(2 * max_norm)) + np.float32(min_level_db)
+        return (S + np.float32(ref_level_db)).astype(np.float32)
+    if clip_norm:
+        S = np.clip(S, 0, max_norm)
+    S = (S * np.float32(-min_level_db) / np.float32(max_norm)) + np.float32(min_level_db)
+    return (S + np.float32(ref_level_db)).astype(np.float32)
+
+
+def interpolate_vocoder_input(scale_factor, spec):
+    """vocoder/utils/generic_utils.py:11-29: spec [C,T] -> [1,C,T']."""
+    spec = torch.as_tensor(np.asarray(spec)).unsqueeze(0).unsqueeze(0)
+    return F.interpolate(spec, scale_factor=scale_factor, recompute_scale_factor=True, mode="bilinear",
+                         align_corners=False).squeeze(0)
+
+
+def vocoder_handoff(mel_tc, tts_norm, vocoder_norm, sr_tts, sr_vocoder, inference_padding=5):
+    """The chain of utils/synthesizer.py:412-429 for one sentence + the replicate pad of HifiganGenerator.inference
+    (hifigan_generator.py:281): mel_tc is the TTS model output [T, C] (normalised by the TTS AudioProcessor);
+    returns the tensor conv_pre sees, [1, C, T' + 2*pad]."""
+    mel = audio_denormalize(np.asarray(mel_tc).T, **tts_norm).T          # .denormalize(mel.T).T
+    vin = audio_normalize(mel.T, **vocoder_norm)                         # vocoder_ap.normalize(mel.T)
+    scale = [1, sr_vocoder / sr_tts]
+    if scale[1] != 1:
+        vin = interpolate_vocoder_input(scale, vin)
+    else:
+        vin = torch.as_tensor(vin).unsqueeze(0)
+    return F.pad(vin, (inference_padding, inference_padding), "replicate")
+
+
+def wav_to_int16(wav):
+    """save_wav's peak normalisation, utils/audio/numpy_transforms.py:439-441."""
+    wav = np.asarray(wav, dtype=np.float32)
+    wav_norm = wav * (32767 / max(0.01, np.max(np.abs(wav))))
+    return wav_norm.astype(np.int16)

@@ -56,6 +56,7 @@ struct Args {
     int use_base_off;
     int vary;        // rate mode: rotate through `vary` different B start rows (like taps)
     int vstep;       // rows between those starts
+    int kvary;       // rate mode, swizzled layouts: rotate the 32-byte K step inside the swizzle row over `kvary` values (same rows)
     int avary;       // rate mode: rotate through `avary` different (aligned) A tiles, 4 KB apart (like per-tap weight blocks)
     const float* A;  // [128][KW]   (KW = floats per row of the layout: 8, 16, 32; none: 8)
     const float* B;  // [ROWS_B][KW]
@@ -127,17 +128,26 @@ __global__ void __launch_bounds__(192, 1) k_mma(const Args a) {
             bdesc0 = 0;
             rowb = SW;
         }
-        long long t0 = clock64();
-        for (int i = 0; i < a.nmma; ++i) {
-            const int sh = a.shift_rows + (a.vary > 1 ? (i % a.vary) * a.vstep : 0);
-            const uint64_t aoff = a.avary > 1 ? (uint64_t)(((i % a.avary) * 4096) >> 4) : 0;   // next 128-row A tile
-            uint64_t bdesc;
-            if (a.layout == 0) bdesc = bdesc0 + (uint64_t)sh;     // 16-byte rows: +1 per row in the address field
+        // descriptors of one 8-MMA round are built BEFORE the timed loop and the round is fully unrolled: the issuing
+        // thread's own index arithmetic must not be what is measured (a first version computed i % vary in the loop and
+        // was issue-bound at ~237 cycles per MMA whatever the operands did)
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int sh = a.shift_rows + (a.vary > 1 ? (j % a.vary) * a.vstep : 0);
+            ad[j] = adesc + (a.avary > 1 ? (uint64_t)(((j % a.avary) * 4096) >> 4) : 0);
+            if (a.layout == 0) bd[j] = bdesc0 + (uint64_t)sh;
             else {
-                const uint32_t sb = bbase + sh * rowb + a.kstep * 32;
-                bdesc = make_desc(sb, 16, 8 * SW, a.layout, a.use_base_off ? ((sb >> 7) & 7) : 0);
+                const uint32_t sb = bbase + sh * rowb + (a.kvary > 1 ? (j % a.kvary) : a.kstep) * 32;
+                bd[j] = make_desc(sb, 16, 8 * SW, a.layout, a.use_base_off ? ((sb >> 7) & 7) : 0);
+                if (a.kvary > 1) ad[j] = make_desc(abase + (j % a.kvary) * 32, 16, 8 * SW, a.layout, 0);
             }
-            mma_tf32(tmem, adesc + aoff, bdesc, idesc, i == 0 ? 0u : 1u);
+        }
+        long long t0 = clock64();
+        mma_tf32(tmem, ad[0], bd[0], idesc, 0u);
+        for (int i = 8; i < a.nmma; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_tf32(tmem, ad[j], bd[j], idesc, 1u);
         }
         mma_commit(smem_u32(bar));
         mbar_wait(smem_u32(bar), 0);
@@ -181,26 +191,27 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dcyc, sizeof(long long) * sms));
     // ------------------------------------------------------------ (1) rate
     printf("# rate: cycles per tcgen05.mma kind::tf32 M=128, K=8 (all %d SMs issuing, nmma=4096)\n", sms);
-    struct Case { int shift, vary, vstep, avary; const char* what; };
+    struct Case { int shift, vary, vstep, avary, kvary; const char* what; };
     const Case cases[] = {
-        {0, 1, 0, 1, "fixed descriptors, aligned"},
-        {3, 1, 0, 1, "fixed descriptors, B start 3 rows off an 8-row group"},
-        {4, 1, 0, 1, "fixed descriptors, B start 4 rows off"},
-        {0, 4, 8, 1, "B rotates over 4 starts, 8 rows apart (aligned)"},
-        {0, 4, 3, 1, "B rotates over 4 starts, 3 rows apart (the conv tap pattern, dil 3)"},
-        {0, 8, 1, 1, "B rotates over 8 starts, 1 row apart (dil 1)"},
-        {0, 4, 4, 1, "B rotates over 4 starts, 4 rows apart"},
-        {0, 1, 0, 4, "A rotates over 4 aligned tiles, B fixed aligned"},
-        {0, 4, 3, 4, "A rotates (aligned), B rotates 3 rows apart"},
+        {0, 1, 0, 1, 1, "fixed descriptors, aligned"},
+        {3, 1, 0, 1, 1, "fixed descriptors, B start 3 rows off an 8-row group"},
+        {0, 4, 8, 1, 1, "B rotates over 4 starts, 8 rows apart (aligned)"},
+        {0, 4, 3, 1, 1, "B rotates over 4 starts, 3 rows apart (the conv tap pattern, dil 3)"},
+        {0, 8, 1, 1, 1, "B rotates over 8 starts, 1 row apart (dil 1)"},
+        {0, 1, 0, 4, 1, "A rotates over 4 aligned tiles, B fixed aligned"},
+        {0, 4, 3, 4, 1, "A rotates (aligned), B rotates 3 rows apart"},
+        {0, 1, 0, 1, 4, "A and B step through the 4 K offsets of one swizzle row (same rows; GEMM K loop)"},
+        {0, 4, 3, 1, 4, "K offsets rotate AND B start rotates 3 rows apart"},
     };
     for (int layout : {0, 6, 4, 2})
         for (int N : {128, 256})
             for (const Case& cs : cases) {
                 Args a; memset(&a, 0, sizeof(a));
-                a.mode = 0; a.layout = layout; a.N = N; a.nmma = 4096; a.vary = cs.vary; a.vstep = cs.vstep; a.avary = cs.avary;
+                a.mode = 0; a.layout = layout; a.N = N; a.nmma = 4096; a.vary = cs.vary; a.vstep = cs.vstep; a.avary = cs.avary; a.kvary = cs.kvary;
                 a.shift_rows = cs.shift; a.rows_b = 320; a.cyc = dcyc;
                 a.use_base_off = 0;
                 if (layout != 0 && layout != 6 && cs.avary > 1) continue;   // wide-row A tiles do not fit the 32 KB A region 4x
+                if (cs.kvary > 1 && layout != 2) continue;                  // K offsets inside a row: 128-byte rows only
                 cudaEvent_t e0, e1;
                 CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
                 k_mma<<<sms, 192, SMEM>>>(a);   // warm-up

@@ -62,6 +62,12 @@ class Conv1dConfigC(ctypes.Structure):
                                             "transposed", "stride")]
 
 
+class AudioNormC(ctypes.Structure):
+    _fields_ = [("signal_norm", ctypes.c_int), ("symmetric_norm", ctypes.c_int), ("clip_norm", ctypes.c_int),
+                ("max_norm", ctypes.c_float), ("min_level_db", ctypes.c_float), ("ref_level_db", ctypes.c_float),
+                ("scaler_mean", ctypes.c_void_p), ("scaler_scale", ctypes.c_void_p)]
+
+
 DISPATCH_NAMES = {0: "fma", 1: "tc1", 2: "tc2", 3: "tc3", 4: "tc3_staged", 5: "tc3_grouped", 6: "row1", 7: "resblock"}
 
 
@@ -82,6 +88,17 @@ def _declare(lib):
     lib.b200tts_conv1d_out_len.argtypes = [vp, ci]
     lib.b200tts_conv1d_forward.restype = ci
     lib.b200tts_conv1d_forward.argtypes = [vp, vp, ci, ci, ctypes.c_float, vp, ctypes.c_float, ci, ctypes.c_float, vp, vp]
+    lib.b200tts_hifigan_forward_peak.restype = ci
+    lib.b200tts_hifigan_forward_peak.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp, sz, vp]
+    lib.b200tts_vocoder_input_len.restype = ci
+    lib.b200tts_vocoder_input_len.argtypes = [ci, ctypes.c_float, ci]
+    lib.b200tts_vocoder_input.restype = ci
+    lib.b200tts_vocoder_input.argtypes = [vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ctypes.POINTER(AudioNormC),
+                                          ctypes.POINTER(AudioNormC), ctypes.c_float, ci, vp, ci, vp]
+    lib.b200tts_absmax.restype = ci
+    lib.b200tts_absmax.argtypes = [vp, ctypes.c_longlong, vp, vp]
+    lib.b200tts_to_int16.restype = ci
+    lib.b200tts_to_int16.argtypes = [vp, ctypes.c_longlong, vp, vp, vp]
     lib.b200tts_mas_workspace_bytes.restype = sz
     lib.b200tts_mas_workspace_bytes.argtypes = [ci, ci, ci]
     lib.b200tts_mas.restype = ci

@@ -90,6 +90,26 @@ int b200tts_hifigan_forward(const b200tts_hifigan* h, const float* x, const floa
     return h->impl.forward(x, g, B, T, wav, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int b200tts_hifigan_forward_peak(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
+                                 uint32_t* peak_bits, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) { set_error("hifigan_forward_peak: null handle"); return 1; }
+    return h->impl.forward(x, g, B, T, wav, workspace, workspace_bytes, (cudaStream_t)stream, peak_bits);
+}
+
+int b200tts_vocoder_input_len(int T, float scale_factor, int padding) { return vocoder_input_len(T, scale_factor, padding); }
+int b200tts_vocoder_input(const float* x, long long x_batch_stride, int x_channel_stride, int x_time_stride, int B, int C,
+                          int T, const b200tts_audio_norm* denormalize, const b200tts_audio_norm* normalize,
+                          float scale_factor, int padding, float* y, int y_pitch, void* stream) {
+    return launch_vocoder_input(x, x_batch_stride, x_channel_stride, x_time_stride, B, C, T, denormalize, normalize,
+                                scale_factor, padding, y, y_pitch, (cudaStream_t)stream);
+}
+int b200tts_absmax(const float* x, long long n, uint32_t* peak_bits, void* stream) {
+    return launch_absmax(x, n, peak_bits, (cudaStream_t)stream);
+}
+int b200tts_to_int16(const float* x, long long n, const uint32_t* peak_bits, int16_t* out, void* stream) {
+    return launch_to_int16(x, n, peak_bits, out, (cudaStream_t)stream);
+}
+
 int b200tts_flow_create(const b200tts_flow_config* cfg, const float* const* weights, int num_weights,
                         b200tts_flow** out) {
     if (!cfg || !weights || !out) { set_error("flow_create: null argument"); return 1; }

@@ -117,6 +117,7 @@ struct ConvIO {
     float act_param = 0.f;
     int flags = 0;
     int B = 1;
+    unsigned* peak_bits = nullptr;   // single-row tanh kernel only: atomicMax of |y| (as float bits) over everything stored
 };
 
 // Host weights in PyTorch layout.  conv: w[Cout][Cin][K];  transposed: w[Cin][Cout][Kt].

@@ -15,6 +15,7 @@
 // broadcasts), accumulating row pairs with fma.rn.f32x2 (SASS FFMA2, x as broadcast scalar).
 // Bias / conditioning / gate / residual / mask / MRF-accumulate epilogues are fused.
 #include "common.cuh"
+#include "engines.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv_tc3.cuh"
@@ -557,46 +558,56 @@ template <int K>
 __global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restrict__ x, long long x_bs, int x_cs, int Cin,
                                                           int T, const float* __restrict__ w, int w_stride,
                                                           const float* __restrict__ bias, float slope, int act,
-                                                          float* __restrict__ y, long long y_bs) {
+                                                          float* __restrict__ y, long long y_bs,
+                                                          unsigned* __restrict__ peak_bits) {
     constexpr int PAD = (K - 1) / 2, NL = (4 + 4 + (K - 1 - PAD) + 3) / 4;   // float4 loads covering [t0 - 4, t0 + 4 + K-1-PAD)
     extern __shared__ float ws[];
     for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) ws[i] = w[(size_t)i * w_stride];
     __syncthreads();
     const int b = blockIdx.y;
     const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (t0 >= T) return;
-    const float* xb = x + b * x_bs + t0;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool valid = t0 < T;
+    if (!valid && !peak_bits) return;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        const float* xb = x + b * x_bs + t0;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-    for (int ci = 0; ci < Cin; ++ci) {
-        const float* xr = xb + (long long)ci * x_cs;
-        float win[4 * NL];
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float* xr = xb + (long long)ci * x_cs;
+            float win[4 * NL];
 #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            const int t = t0 - 4 + 4 * l;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // T % 4 == 0: all in or all out
-            win[4 * l] = v.x; win[4 * l + 1] = v.y; win[4 * l + 2] = v.z; win[4 * l + 3] = v.w;
+            for (int l = 0; l < NL; ++l) {
+                const int t = t0 - 4 + 4 * l;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // T % 4 == 0: all in or all out
+                win[4 * l] = v.x; win[4 * l + 1] = v.y; win[4 * l + 2] = v.z; win[4 * l + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 4 * NL; ++i) win[i] = win[i] > 0.f ? win[i] : win[i] * slope;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float wk = ws[ci * K + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fmaf(wk, win[4 - PAD + j + k], acc[j]);
+            }
         }
+        const float bv = bias[0];
+        float* po = &o.x;
 #pragma unroll
-        for (int i = 0; i < 4 * NL; ++i) win[i] = win[i] > 0.f ? win[i] : win[i] * slope;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float wk = ws[ci * K + k];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fmaf(wk, win[4 - PAD + j + k], acc[j]);
+        for (int j = 0; j < 4; ++j) {
+            float u = acc[j] + bv;
+            if (act == ACT_TANH) u = tanhf(u);
+            po[j] = u;
         }
+        *reinterpret_cast<float4*>(y + b * y_bs + t0) = o;
     }
-    const float bv = bias[0];
-    float4 o;
-    float* po = &o.x;
+    if (peak_bits) {   // save_wav's max|wav| (numpy_transforms.py:439) folded into the store: one atomic per warp
+        float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w)));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float u = acc[j] + bv;
-        if (act == ACT_TANH) u = tanhf(u);
-        po[j] = u;
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(peak_bits, __float_as_uint(m));
     }
-    *reinterpret_cast<float4*>(y + b * y_bs + t0) = o;
 }
 
 // ------------------------------------------------------------------ host: launch
@@ -776,11 +787,11 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         t.B = io.B; t.n_ttiles = (a.Tq + tc3::TT2 - 1) / tc3::TT2; t.n_rtiles = n_rtiles;
         t.err = g_tc_err;
         static int staged = -1;
-        if (staged < 0) { const char* e = getenv("B200TTS_STAGED"); staged = (e && atoi(e)) ? 1 : 0; }
+        if (staged < 0) { const char* e = getenv("B200TTS_NO_STAGED"); staged = (e && atoi(e)) ? 0 : 1; }
         size_t smem3 = tc3::smem_bytes3(rows_pad, rows_pad + 4);
-        // opt-in (B200TTS_STAGED=1) until it has run through the whole GPU suite: measured in the harness it is 13 % faster
-        // on the epilogue-bound K <= 3 layers and 5-7 % slower on the MMA-bound K = 7 / 11 ones (its shared-memory
-        // traffic competes with the operand fetch), so only short-kernel layers take it
+        // staged (shared-memory transposed, coalesced) epilogue: 13 % faster on the epilogue-bound K <= 3 layers and 5-7 %
+        // slower on the MMA-bound K = 7 / 11 ones (its shared-memory traffic competes with the operand fetch), so only
+        // short-kernel layers take it.  On by default since r02 (whole GPU suite green); B200TTS_NO_STAGED=1 disables it
         if (staged && L.K <= 3 && L.ups == 1 && !t.gate && t.split == 0 && ((smem3 + 15) / 16 * 16 + tc3::STAGE_BYTES) <= 227 * 1024) {
             t.stage = 1;
             t.stage_off = (int)((smem3 + 15) / 16 * 16);
@@ -885,14 +896,19 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
             if (grid.y <= 65535) {
                 conv1d_row1_kernel<7><<<grid, 256, (size_t)L.Cin * L.K * 4, st>>>(a.x, a.x_bs, a.x_cs, L.Cin, a.Tout, L.w,
                                                                                  L.co_tile, L.bias, a.in_slope, a.act, a.y,
-                                                                                 a.y_bs);
+                                                                                 a.y_bs, io.peak_bits);
                 count_launch();
                 dispatch_note(DISPATCH_ROW1);
                 B200_CUDA_OK(cudaGetLastError());
                 return 0;
             }
         }
-        return launch_cic<KEPI_TANH>(a, L.co_tile, io.B, L.RowsPad, st);
+        if (int rc = launch_cic<KEPI_TANH>(a, L.co_tile, io.B, L.RowsPad, st)) return rc;
+        if (io.peak_bits) {   // the streaming kernel was not eligible: fold the peak in a pass of its own
+            B200_REQUIRE(a.y_cs == a.Tout && a.y_bs == (long long)L.Rows * a.Tout, "launch_conv: peak needs a dense output");
+            return launch_absmax(a.y, (long long)io.B * L.Rows * a.Tout, io.peak_bits, st);
+        }
+        return 0;
     }
     if (int rc = try_launch_tc(L, io, a, st); rc != -1) return rc;
     const bool plain = L.ups == 1 && !io.res && a.scale == 1.f && a.post_div == 1.f &&

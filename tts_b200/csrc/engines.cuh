@@ -19,8 +19,10 @@ struct Hifigan {
     void stage_dims(int T, std::vector<int>& C, std::vector<int>& L) const;
     size_t workspace_bytes(int B, int T) const;
     int out_len(int T) const;
+    // peak_bits (nullable): device word that conv_post's store folds max|wav| into (atomicMax on the float's bits; the
+    // caller zeroes it) -- the first half of save_wav's peak normalisation without another pass over the waveform
     int forward(const float* x, const float* g, int B, int T, float* wav, void* ws, size_t ws_bytes,
-                cudaStream_t st) const;
+                cudaStream_t st, unsigned* peak_bits = nullptr) const;
 };
 
 struct WaveNet {
@@ -131,6 +133,14 @@ int launch_durations(const float* logw, const float* x_mask, float length_scale,
 int launch_expand_prior(const float* cum, const float* x_mask, const long long* y_lengths, const float* stats,
                         const float* noise, float noise_scale, int B, int Tx, int Ty, int C, float* attn, float* m_p,
                         float* logs_p, float* z_p, float* y_mask, cudaStream_t st);
+
+// vocoder hand-off (vocoder_io.cu)
+int vocoder_input_len(int T, float scale_factor, int pad);
+int launch_vocoder_input(const float* x, long long x_bs, int x_cs, int x_ts, int B, int C, int T,
+                         const b200tts_audio_norm* denorm, const b200tts_audio_norm* norm, float scale_factor, int pad,
+                         float* y, int y_pitch, cudaStream_t st);
+int launch_absmax(const float* x, long long n, unsigned* peak_bits, cudaStream_t st);
+int launch_to_int16(const float* x, long long n, const unsigned* peak_bits, short* out, cudaStream_t st);
 
 // monotonic alignment search (mas.cu)
 size_t mas_workspace_bytes(int B, int Tx, int Ty);

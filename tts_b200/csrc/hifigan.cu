@@ -103,7 +103,7 @@ int Hifigan::out_len(int T) const {
 }
 
 int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, void* ws, size_t ws_bytes,
-                     cudaStream_t st) const {
+                     cudaStream_t st, unsigned* peak_bits) const {
     B200_REQUIRE(x && wav && ws, "hifigan_forward: null pointer");
     B200_REQUIRE((c.cond_channels > 0) == (g != nullptr) || c.cond_channels == 0,
                  "hifigan_forward: model has cond_channels=%d but g is null", c.cond_channels);
@@ -208,6 +208,7 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
         io.x = cur; io.x_bs = (long long)curC * curPitch; io.x_cs = curPitch; io.Tin = curL; io.in_slope = 0.01f;
         io.y = wav; io.y_bs = (long long)c.out_channels * curL; io.y_cs = curL; io.Tout = curL; io.B = B;
         io.act = ACT_TANH;
+        io.peak_bits = peak_bits;
         if ((rc = launch_conv(conv_post, io, st))) return rc;
     }
     return 0;

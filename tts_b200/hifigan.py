@@ -175,9 +175,10 @@ class HifiganGenerator(nn.Module):
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
-    def forward(self, x, g=None):
+    def forward(self, x, g=None, peak=None):
         """x [B, C, T] (CUDA), g [B, cond, 1] -> waveform [B, out_channels, T*prod(upsample_factors)]
-        (hifigan_generator.py:236-265)."""
+        (hifigan_generator.py:236-265).  ``peak`` (optional int32[1] device word, zeroed by the caller): conv_post folds
+        max|wav| into it while storing -- the first half of save_wav's peak normalisation (tts_b200.vocoder.wav_to_int16)."""
         _lib.require_cuda(x, "x")
         if hasattr(self, "cond_layer") and g is None:
             raise ValueError("tts_b200.HifiganGenerator: model has a cond_layer but g is None")
@@ -195,16 +196,23 @@ class HifiganGenerator(nn.Module):
             wav = torch.empty((b, self._cfg["out_channels"], tout), dtype=torch.float32, device=x.device)
             nbytes = L.b200tts_hifigan_workspace_bytes(h, b, t)
             ws = _lib.workspace(x.device, nbytes, "hifigan")
-            rc = L.b200tts_hifigan_forward(h, _lib.ptr(x), _lib.ptr(gl), b, t, _lib.ptr(wav), _lib.ptr(ws),
-                                           ctypes.c_size_t(ws.numel()), _lib.stream_ptr(x.device))
+            if peak is None:
+                rc = L.b200tts_hifigan_forward(h, _lib.ptr(x), _lib.ptr(gl), b, t, _lib.ptr(wav), _lib.ptr(ws),
+                                               ctypes.c_size_t(ws.numel()), _lib.stream_ptr(x.device))
+            else:
+                rc = L.b200tts_hifigan_forward_peak(h, _lib.ptr(x), _lib.ptr(gl), b, t, _lib.ptr(wav), _lib.ptr(peak),
+                                                    _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr(x.device))
         _lib.check(rc, "hifigan_forward")
         return wav
 
     @torch.no_grad()
     def inference(self, c):
         """Replicate-pad ``inference_padding`` frames each side, then forward (hifigan_generator.py:267-282)."""
+        from .vocoder import AudioNorm, vocoder_input
         c = c.to(self.conv_pre.bias.device)
-        c = torch.nn.functional.pad(c, (self.inference_padding, self.inference_padding), "replicate")
+        # the replicate padding comes from the hand-off kernel (one pass together with any re-normalisation /
+        # interpolation a caller folds in through tts_b200.vocoder.vocoder_input), not from a torch op
+        c = vocoder_input(c, AudioNorm.identity(), AudioNorm.identity(), padding=self.inference_padding)
         return self.forward(c)
 
     def remove_weight_norm(self):

@@ -429,6 +429,30 @@ class Vits(nn.Module):
             self.eval()
             assert not self.training
 
+    def load_fairseq_checkpoint(self, config, checkpoint_dir, eval=False, strict=True):  # pylint: disable=redefined-builtin
+        """VITS checkpoints released by fairseq (MMS): ``config.json`` + ``G_100000.pth`` + ``vocab.txt``
+        (vits.py:1727-1769): sets the sample rate, builds the character tokenizer from the vocabulary, resizes the
+        text embedding to it and loads the re-keyed weights."""
+        import json
+        import os
+
+        from .text import FairseqVocab, TTSTokenizer, basic_cleaners, rehash_fairseq_vits_checkpoint
+        with open(os.path.join(checkpoint_dir, "config.json"), "r", encoding="utf-8") as f:
+            config_org = json.load(f)
+        _get(self.config, "audio").sample_rate = config_org["data"]["sampling_rate"]
+        vocab = FairseqVocab(os.path.join(checkpoint_dir, "vocab.txt"))
+        self.text_encoder.emb = nn.Embedding(vocab.num_chars, _get(config, "model_args").hidden_channels)
+        self.text_encoder._cfg["n_vocab"] = vocab.num_chars
+        self.tokenizer = TTSTokenizer(use_phonemes=False, text_cleaner=basic_cleaners, characters=vocab, phonemizer=None,
+                                      add_blank=config_org["data"]["add_blank"], use_eos_bos=False)
+        new_chk = rehash_fairseq_vits_checkpoint(os.path.join(checkpoint_dir, "G_100000.pth"))
+        new_chk = {k: v for k, v in new_chk.items() if not k.startswith("disc.")}   # training-only sub-module
+        self.load_state_dict(new_chk, strict=strict)
+        self.repack()
+        if eval:
+            self.eval()
+            assert not self.training
+
     def repack(self):
         for m in self.modules():
             if isinstance(m, EngineModule) and m is not self:
