@@ -380,6 +380,11 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     model = build_model().to(dev)
+    # ragged batches: skip the padded frames of the batch in the flow and the decoder (every valid sample stays
+    # bit-identical, tests/test_ragged_gpu.py; the padded tail of model_outputs, which no caller keeps and the metric
+    # never counted, becomes zero instead of the decoder's response to zero input).  BENCH_DENSE=1 measures the
+    # reference's dense batch semantics instead.
+    model.trim_padding = not os.environ.get("BENCH_DENSE")
     tokens_h, lengths_h, sdp_noise_h = make_batch(rank)
     tokens_pin, lengths_pin, noise_pin = tokens_h.pin_memory(), lengths_h.pin_memory(), sdp_noise_h.pin_memory()
     tokens_d, lengths_d, noise_d = tokens_h.to(dev), lengths_h.to(dev), sdp_noise_h.to(dev)
@@ -531,7 +536,15 @@ def run_cuda(args):
         peaks = load_peaks()
         value = total_samples / t_resident_max
         e2e_value = total_e2e_samples / t_e2e_max
-        dec_tflops = padded_samples * HIFIGAN_FLOP_PER_SAMPLE / (dec_ms / 1e3) / 1e12 if dec_ms > 0 else None
+        # algorithmic work of the decoder pass: the frames it really computes (valid frames + the exactness margin per
+        # utterance in ragged mode, every padded frame in dense mode)
+        if model.trim_padding:
+            margin = _lib.lib().b200tts_hifigan_margin_frames(model.waveform_decoder._handle)
+            computed_samples = total_samples / max(world, 1) + args.steps * B_PER_GPU * margin * 256
+            computed_samples = min(computed_samples, padded_samples)
+        else:
+            computed_samples = padded_samples
+        dec_tflops = computed_samples * HIFIGAN_FLOP_PER_SAMPLE / (dec_ms / 1e3) / 1e12 if dec_ms > 0 else None
         h2d = tokens_pin.numel() * 8 + lengths_pin.numel() * 8 + noise_pin.numel() * 4
         if cpu is None:   # developer A/B runs (BENCH_SKIP_CPU) and N > 1: the contract's cpu_baseline is an N = 1 item
             cpu_nb, cpu_v, cpu_sec, cpu_samples, cores = 0, None, 0.0, 0, 0
@@ -554,6 +567,10 @@ def run_cuda(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "vits_e2e_inference_b32_t64 (BASELINE configs[1])", "batch_per_gpu": B_PER_GPU,
                        "tokens": T_TEXT, "frames_padded_per_step": frames_padded // args.steps,
+                       "frames_valid_per_step": int(total_samples / args.steps / 256),
+                       "padding": ("ragged: padded frames of the batch are skipped in flow + decoder, valid samples bit-identical "
+                                   "to the dense call, padded tail zero (Vits.trim_padding)") if model.trim_padding else
+                                  "dense: the reference's batch semantics, padded tail computed",
                        "parallelism": f"dp{world}", "l2": "256 MiB buffer written between timed steps (outside the events)",
                        "rtf": (t_resident_max / args.steps) / (total_samples / args.steps / SR),
                        "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},

@@ -114,11 +114,19 @@ int b200tts_hifigan_out_len(const b200tts_hifigan* h, int T);
 int b200tts_hifigan_forward(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
                             void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same as b200tts_hifigan_forward; additionally conv_post's store folds max|wav| over everything it writes into
- * *peak_bits (atomicMax on the float's bit pattern; the caller zeroes the word first, several calls may share it):
- * the first half of save_wav's peak normalisation, TTS/utils/audio/numpy_transforms.py:439, without another pass. */
-int b200tts_hifigan_forward_peak(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
-                                 uint32_t* peak_bits, void* workspace, size_t workspace_bytes, void* stream);
+/* b200tts_hifigan_forward with two optional extras (either may be NULL):
+ *  - frame_lengths, device int32 [B]: valid frames per row of a padded batch.  Padded frames are then neither computed nor
+ *    read: every launch stops a layer-specific margin past a row's end (the receptive field of the layers that still
+ *    follow; b200tts_hifigan_margin_frames() is the largest, at the input rate), so every sample below
+ *    frame_lengths[b] * prod(upsample_factors) is BIT-IDENTICAL to the dense call and the rest of the row is zero
+ *    (the dense call, like the reference, fills it with the network's response to zero input, which no caller keeps).
+ *  - peak_bits: conv_post's store folds max|wav| over everything it writes into *peak_bits (atomicMax on the float's
+ *    bit pattern; the caller zeroes the word first, several calls may share it): the first half of save_wav's peak
+ *    normalisation, TTS/utils/audio/numpy_transforms.py:439, without another pass. */
+int b200tts_hifigan_forward_ex(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
+                               const int32_t* frame_lengths, uint32_t* peak_bits, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int b200tts_hifigan_margin_frames(const b200tts_hifigan* h);
 
 /* ---- hand-off around a standalone vocoder ---------------------------------------------------------
  * b200tts_vocoder_input replaces, in one pass on the device, what Synthesizer.tts does on the host between the TTS
@@ -178,6 +186,12 @@ void b200tts_flow_destroy(b200tts_flow* h);
 size_t b200tts_flow_workspace_bytes(const b200tts_flow* h, int B, int T);
 int b200tts_flow_reverse(const b200tts_flow* h, float* z, const float* mask, const float* g, int B, int T,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* Same with frame_lengths (device int32 [B], = the row sums of mask): rows are neither computed nor read past their
+ * length.  Everything in the flow is re-masked, so frames below frame_lengths[b] are bit-identical to the dense call;
+ * beyond a row's end z keeps its input values (the dense call writes zeros there): mask z afterwards. */
+int b200tts_flow_reverse_ragged(const b200tts_flow* h, float* z, const float* mask, const float* g,
+                                const int32_t* frame_lengths, int B, int T, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* ---- latent upsampling (VitsArgs.encoder_sample_rate) -----------------------------------------
  * Replaces torch.nn.functional.interpolate(z, scale_factor=[f], mode="linear") in Vits.upsampling_z,

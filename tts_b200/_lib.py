@@ -88,8 +88,12 @@ def _declare(lib):
     lib.b200tts_conv1d_out_len.argtypes = [vp, ci]
     lib.b200tts_conv1d_forward.restype = ci
     lib.b200tts_conv1d_forward.argtypes = [vp, vp, ci, ci, ctypes.c_float, vp, ctypes.c_float, ci, ctypes.c_float, vp, vp]
-    lib.b200tts_hifigan_forward_peak.restype = ci
-    lib.b200tts_hifigan_forward_peak.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp, sz, vp]
+    lib.b200tts_hifigan_forward_ex.restype = ci
+    lib.b200tts_hifigan_forward_ex.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp, vp, sz, vp]
+    lib.b200tts_hifigan_margin_frames.restype = ci
+    lib.b200tts_hifigan_margin_frames.argtypes = [vp]
+    lib.b200tts_flow_reverse_ragged.restype = ci
+    lib.b200tts_flow_reverse_ragged.argtypes = [vp, vp, vp, vp, vp, ci, ci, vp, sz, vp]
     lib.b200tts_vocoder_input_len.restype = ci
     lib.b200tts_vocoder_input_len.argtypes = [ci, ctypes.c_float, ci]
     lib.b200tts_vocoder_input.restype = ci

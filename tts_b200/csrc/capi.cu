@@ -90,10 +90,14 @@ int b200tts_hifigan_forward(const b200tts_hifigan* h, const float* x, const floa
     return h->impl.forward(x, g, B, T, wav, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int b200tts_hifigan_forward_peak(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
-                                 uint32_t* peak_bits, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!h) { set_error("hifigan_forward_peak: null handle"); return 1; }
-    return h->impl.forward(x, g, B, T, wav, workspace, workspace_bytes, (cudaStream_t)stream, peak_bits);
+int b200tts_hifigan_forward_ex(const b200tts_hifigan* h, const float* x, const float* g, int B, int T, float* wav,
+                               const int32_t* frame_lengths, uint32_t* peak_bits, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!h) { set_error("hifigan_forward_ex: null handle"); return 1; }
+    return h->impl.forward(x, g, B, T, wav, workspace, workspace_bytes, (cudaStream_t)stream, peak_bits, frame_lengths);
+}
+int b200tts_hifigan_margin_frames(const b200tts_hifigan* h) {   // frames past a row's end the ragged schedule still computes
+    return h ? h->impl.need_P : 0;
 }
 
 int b200tts_vocoder_input_len(int T, float scale_factor, int padding) { return vocoder_input_len(T, scale_factor, padding); }
@@ -140,6 +144,12 @@ int b200tts_flow_reverse(const b200tts_flow* h, float* z, const float* mask, con
                          void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) { set_error("flow_reverse: null handle"); return 1; }
     return h->impl.reverse(z, mask, g, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int b200tts_flow_reverse_ragged(const b200tts_flow* h, float* z, const float* mask, const float* g,
+                                const int32_t* frame_lengths, int B, int T, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (!h) { set_error("flow_reverse_ragged: null handle"); return 1; }
+    return h->impl.reverse(z, mask, g, B, T, workspace, workspace_bytes, (cudaStream_t)stream, frame_lengths);
 }
 
 int b200tts_text_encoder_create(const b200tts_text_encoder_config* cfg, const float* const* weights,

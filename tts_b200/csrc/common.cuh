@@ -118,6 +118,11 @@ struct ConvIO {
     int flags = 0;
     int B = 1;
     unsigned* peak_bits = nullptr;   // single-row tanh kernel only: atomicMax of |y| (as float bits) over everything stored
+    // ragged batch (null: dense).  lens[b] = valid FRAMES of row b; this launch's output is only computed below
+    // lens[b] * rate_out + need_out (time steps of y; for a transposed conv `rate_out` counts GEMM columns, i.e. input
+    // steps), its input is read as zero from lens[b] * rate_in + need_in on.  Honoured by the persistent tcgen05 kernels
+    // and the single-row kernel; the FMA tile kernel computes the full tensor (valid samples are identical either way).
+    const int* lens = nullptr; int rate_out = 1, need_out = 0, rate_in = 1, need_in = 0;
 };
 
 // Host weights in PyTorch layout.  conv: w[Cout][Cin][K];  transposed: w[Cin][Cout][Kt].

@@ -82,6 +82,7 @@ struct ConvKArgs {
     float* y2; long long y2_bs; int y2_cs; int split;
     float scale; float post_div; int act; float act_param; int flags;
     int XS;
+    const int* lens; int rate_out, need_out, rate_in, need_in;
 };
 
 enum : int { KEPI_GENERIC = 0, KEPI_GATE = 1, KEPI_TANH = 2, KEPI_PLAIN = 3 };
@@ -559,14 +560,28 @@ __global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restric
                                                           int T, const float* __restrict__ w, int w_stride,
                                                           const float* __restrict__ bias, float slope, int act,
                                                           float* __restrict__ y, long long y_bs,
-                                                          unsigned* __restrict__ peak_bits) {
+                                                          unsigned* __restrict__ peak_bits, const int* __restrict__ lens,
+                                                          int rate, int need) {
     constexpr int PAD = (K - 1) / 2, NL = (4 + 4 + (K - 1 - PAD) + 3) / 4;   // float4 loads covering [t0 - 4, t0 + 4 + K-1-PAD)
     extern __shared__ float ws[];
     for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) ws[i] = w[(size_t)i * w_stride];
     __syncthreads();
     const int b = blockIdx.y;
+    // ragged batch: row b holds data below Tb only (a multiple of 4); samples from Tb on are written as zeros and the
+    // input is read as zero there -- so the padded tail of the waveform is clean and costs no bandwidth
+    int Tb = T;
+    if (lens) {
+        const long long e = ((long long)lens[b] * rate + need + 3) / 4 * 4;
+        Tb = (int)(e < (long long)T ? (e > 0 ? e : 0) : (long long)T);
+    }
+    if ((int)(blockIdx.x * blockDim.x) * 4 >= Tb && !peak_bits) {        // whole block beyond the row: zero fill and leave
+        const int tz = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (tz < T) *reinterpret_cast<float4*>(y + b * y_bs + tz) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const bool valid = t0 < T;
+    const bool valid = t0 < Tb;
+    if (!valid && t0 < T) *reinterpret_cast<float4*>(y + b * y_bs + t0) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!valid && !peak_bits) return;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
@@ -580,7 +595,7 @@ __global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restric
             for (int l = 0; l < NL; ++l) {
                 const int t = t0 - 4 + 4 * l;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // T % 4 == 0: all in or all out
+                if (t >= 0 && t < Tb) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // Tb % 4 == 0: all in or all out
                 win[4 * l] = v.x; win[4 * l + 1] = v.y; win[4 * l + 2] = v.z; win[4 * l + 3] = v.w;
             }
 #pragma unroll
@@ -700,6 +715,17 @@ static cudaError_t launch_tc3(tc3::Tc3Kernel k, int grid, size_t smem, cudaStrea
     cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, k, t);
 }
+// ragged batches: the prefix table lives behind everything else in dynamic shared memory (when it still fits)
+static void set_ragged(tc3::Tc3Args& t, const ConvKArgs& a, size_t& smem) {
+    t.lens = nullptr; t.rate_q = 1; t.need_q = 0; t.rate_in = 1; t.need_in = 0; t.pref_off = 0;
+    if (!a.lens) return;
+    const size_t off = (smem + 15) / 16 * 16, extra = tc3::ragged_table_bytes(t.B);
+    if (off + extra > 227 * 1024) return;           // enormous batch: fall back to the dense schedule (still correct)
+    t.lens = a.lens; t.rate_q = a.rate_out; t.need_q = a.need_out; t.rate_in = a.rate_in; t.need_in = a.need_in;
+    t.pref_off = (int)off;
+    smem = off + extra;
+}
+
 static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
     static int enabled = -1, v2_enabled = -1, grouped_enabled = 1;
     if (enabled < 0) {
@@ -757,9 +783,11 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             t.rows_pad = rp; t.raw_w = rp + 4;
             t.B = io.B; t.n_ttiles = (a.Tq + t.tstep - 1) / t.tstep; t.n_rtiles = 1;
             t.err = g_tc_err;
+            size_t smemg = tc3::smem_bytes3(rp, rp + 4);
+            set_ragged(t, a, smemg);
             const long long tiles = (long long)t.B * t.n_ttiles;
             const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-            B200_CUDA_OK(launch_tc3(tc3::grouped_kernel(G, L.dil), grid, tc3::smem_bytes3(rp, rp + 4), st, t));
+            B200_CUDA_OK(launch_tc3(tc3::grouped_kernel(G, L.dil), grid, smemg, st, t));
             count_launch();
             dispatch_note(DISPATCH_TC3_GROUPED);
             B200_CUDA_OK(cudaGetLastError());
@@ -797,6 +825,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             t.stage_off = (int)((smem3 + 15) / 16 * 16);
             smem3 = (size_t)t.stage_off + tc3::STAGE_BYTES;
         }
+        set_ragged(t, a, smem3);
         const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
         const int grid = (int)(tiles < num_sms ? tiles : num_sms);
         B200_CUDA_OK(launch_tc3(t.stage ? tc3::conv1d_tc3s_kernel : tc3::conv1d_tc3_kernel, grid, smem3, st, t));
@@ -875,6 +904,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
     a.ymask = io.ymask; a.ymask_bs = io.ymask_bs;
     a.y2 = io.y2; a.y2_bs = io.y2_bs; a.y2_cs = io.y2_cs; a.split = io.split;
     a.scale = io.scale; a.post_div = io.post_div; a.act = io.act; a.act_param = io.act_param; a.flags = io.flags;
+    a.lens = io.lens; a.rate_out = io.rate_out; a.need_out = io.need_out; a.rate_in = io.rate_in; a.need_in = io.need_in;
     if (a.Tq <= 0 || io.B <= 0) return 0;
     B200_REQUIRE(!(a.flags & (EPI_MASK_PRE | EPI_MASK_POST | EPI_SPLIT)) || io.ymask,
                  "launch_conv: masked/split epilogue needs ymask");
@@ -896,7 +926,8 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
             if (grid.y <= 65535) {
                 conv1d_row1_kernel<7><<<grid, 256, (size_t)L.Cin * L.K * 4, st>>>(a.x, a.x_bs, a.x_cs, L.Cin, a.Tout, L.w,
                                                                                  L.co_tile, L.bias, a.in_slope, a.act, a.y,
-                                                                                 a.y_bs, io.peak_bits);
+                                                                                 a.y_bs, io.peak_bits, a.lens, a.rate_out,
+                                                                                 a.need_out);
                 count_launch();
                 dispatch_note(DISPATCH_ROW1);
                 B200_CUDA_OK(cudaGetLastError());

@@ -79,11 +79,18 @@ struct Tc3Args {
     int stage;                  // != 0: wide-layer epilogue goes through per-warp shared tiles (coalesced global access)
     int stage_off;              // byte offset of those tiles in dynamic shared memory (8 warps x 5120 B)
     int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA
+    // ---- ragged batches (null lens: every row spans the full tensor).  Row b only has tiles for GEMM columns below
+    // min(Tq, lens[b] * rate_q + need_q) and its input is read as zero from min(Tin, lens[b] * rate_in + need_in) on:
+    // padded frames cost nothing, and `need` keeps every sample below lens[b] bit-identical to the full computation
+    // (it is the receptive field of the layers that still follow, worked out per launch by the engine).
+    const int* lens; int rate_q, need_q, rate_in, need_in;
+    int pref_off;               // byte offset in dynamic shared memory of the (B + 1)-entry tile prefix table
 };
 
 static inline size_t smem_bytes3(int rows_pad, int raw_w) {
     return (size_t)NRAW * KC2 * raw_w * 4 + (size_t)NA2 * (4 * rows_pad * 16) + (size_t)NB2 * (4 * MROWS * 16) + 512;
 }
+static inline size_t ragged_table_bytes(int B) { return ((size_t)(B + 1) * sizeof(int) + 15) / 16 * 16; }
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -136,7 +143,31 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
     const int nchunks = (a.Cin + KC2 - 1) / KC2;
-    const int tiles_total = a.B * a.n_rtiles * a.n_ttiles;
+    const bool ragged = a.lens != nullptr;
+    int* pref = reinterpret_cast<int*>(smem + a.pref_off);    // pref[b] = first tile of row b (ragged only)
+    if (ragged) {
+        // tiles per row from its own length; exclusive prefix by warp 0 (rows in lane-contiguous chunks).  `lens` was
+        // written several launches ago (durations kernel), so reading it before griddepcontrol.wait is safe.
+        for (int b = tid; b < a.B; b += NTHREADS2) {
+            const long long e = (long long)a.lens[b] * a.rate_q + a.need_q;
+            const int ext = (int)(e < (long long)a.Tq ? (e > 0 ? e : 0) : (long long)a.Tq);
+            pref[b + 1] = ((ext + a.tstep - 1) / a.tstep) * a.n_rtiles;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int per = (a.B + 31) / 32, lo = lane * per, hi = min(a.B, lo + per);
+            int sum = 0;
+            for (int b = lo; b < hi; ++b) sum += pref[b + 1];
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+            int run = incl - sum;
+            for (int b = lo; b < hi; ++b) { const int c = pref[b + 1]; pref[b + 1] = run + c; run += c; }
+            if (lane == 0) pref[0] = 0;
+        }
+        __syncthreads();
+    }
+    const int tiles_total = ragged ? pref[a.B] : a.B * a.n_rtiles * a.n_ttiles;
     const int my_tiles = (tiles_total > (int)blockIdx.x) ? (tiles_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t acc_cols = (uint32_t)TT2;                     // per accumulator buffer
     const uint32_t ncols = 512;
@@ -164,10 +195,32 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
 
     auto decode = [&](int it, int& b, int& rt, int& q0) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        if (ragged) {
+            int lo = 0, hi = a.B;                   // largest b with pref[b] <= tile (rows without tiles are skipped)
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= tile) lo = mid; else hi = mid; }
+            b = lo;
+            const int local = tile - pref[b], nt = (pref[b + 1] - pref[b]) / a.n_rtiles;
+            rt = local / nt;
+            q0 = (local - rt * nt) * a.tstep;
+            return;
+        }
         const int tt = tile % a.n_ttiles, rest = tile / a.n_ttiles;
         rt = rest % a.n_rtiles;
         b = rest / a.n_rtiles;
         q0 = tt * a.tstep;
+    };
+    // Every CTA of the grid walks the SAME weight tensor; in lock step they would all ask the L2 for the same 8 KB block
+    // at the same time (measured: the few slices holding it saturate while 5/6 of the L2 idles, ~17 B/clk per SM).
+    // Each TILE therefore starts its channel-chunk loop at its own offset -- a function of the tile's coordinates only,
+    // so an output element is always accumulated in the same order whatever the schedule (dense / ragged / grid size).
+    auto chunk_rotation = [&](int b, int q0) -> int {
+        if (a.dbg & 32) return 0;
+        return (int)((unsigned)(b * 5 + q0 / a.tstep) % (unsigned)nchunks);
+    };
+    auto input_extent = [&](int b) -> int {       // columns of x[b] that hold data; beyond it the operand is zero
+        if (!ragged) return a.Tin;
+        const long long e = (long long)a.lens[b] * a.rate_in + a.need_in;
+        return (int)(e < (long long)a.Tin ? (e > 0 ? e : 0) : (long long)a.Tin);
     };
 
     if (warp >= 4 && warp < 8) {
@@ -197,11 +250,21 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             i_raw[e] = (idx < 2 * ROWS) ? (4 * sl) * RAWW + r : -1;
             i_dst[e] = (int)(sl * slabA) + r * 16;
         }
+        int iss_it = -1, iss_b = 0, iss_q0 = 0, iss_Tin = 0, iss_rot = 0;   // the tile the cp.async front is in (decoded once per tile)
+        int tr_it = -1, tr_q0 = 0;                                // the tile the transform is in
         auto issue = [&](int g) {
             if (g < total && !(a.dbg & 1)) {
                 const int it = g / nchunks, c = g - it * nchunks;
-                int b, rt, q0;
-                decode(it, b, rt, q0);
+                if (it != iss_it) {
+                    int rt_;
+                    decode(it, iss_b, rt_, iss_q0);
+                    iss_Tin = input_extent(iss_b);
+                    iss_rot = chunk_rotation(iss_b, iss_q0);
+                    iss_it = it;
+                }
+                const int b = iss_b, q0 = iss_q0, Tin_b = iss_Tin;
+                int ce = c + iss_rot;                                     // this tile's channel-chunk order (see chunk_rotation)
+                if (ce >= nchunks) ce -= nchunks;
                 const int tal = ((q0 - a.pad) & ~3);                     // 16-byte aligned window start (may be < 0)
                 const float* xb = a.x + (long long)b * a.x_bs;
                 const uint32_t dst0 = smem_u32(smRaw + (g % NRAW) * rawStage);
@@ -209,12 +272,12 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 for (int e = 0; e < MAXV; ++e) {
                     if (v_ch[e] < 0) continue;
                     const int t = tal + v_t[e];
-                    const int cg = c * KC2 + v_ch[e];
+                    const int cg = ce * KC2 + v_ch[e];
                     // t is a multiple of 4, so a vector is either wholly before the sequence start (zero fill),
                     // wholly inside, or cut by its end (partial source size, rest zero-filled by the hardware)
                     int nb = 0;
-                    if (cg < a.Cin && t >= 0) nb = 4 * max(0, min(4, a.Tin - t));
-                    const int tsafe = (t >= 0 && t < a.Tin) ? t : 0;
+                    if (cg < a.Cin && t >= 0) nb = 4 * max(0, min(4, Tin_b - t));
+                    const int tsafe = (t >= 0 && t < Tin_b) ? t : 0;
                     const float* src = xb + (long long)(cg < a.Cin ? cg : 0) * a.x_cs + tsafe;
                     cp_async16_zfill(dst0 + (uint32_t)v_off[e] * 4u, src, (uint32_t)nb);
                 }
@@ -230,8 +293,12 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             if (g >= NA2) ok = mbar_wait(BAR(A_EMPTY + as), ((g / NA2) - 1) & 1, a.err);
             if (!ok) break;
             const int it = g / nchunks;
-            int b, rt, q0;
-            decode(it, b, rt, q0);
+            if (it != tr_it) {
+                int b_, rt_;
+                decode(it, b_, rt_, tr_q0);
+                tr_it = it;
+            }
+            const int q0 = tr_q0;
             const int tin0 = q0 - a.pad, off = tin0 - (tin0 & ~3);
             const float* raw = reinterpret_cast<const float*>(smRaw + (g % NRAW) * rawStage) + off;
             unsigned char* base = smA + as * stageA;
@@ -277,12 +344,17 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 int b, rt, q0;
                 decode(it, b, rt, q0);
                 const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.w) + (size_t)rt * total * stageB;
-                for (int j = 0; j < total && ok; ++j, ++gi) {
-                    const int st = gi % NB2;
-                    if (gi >= NB2) ok = mbar_wait(BAR(B_EMPTY + st), ((gi / NB2) - 1) & 1, a.err);
-                    if (!ok) break;
-                    mbar_expect_tx(BAR(B_FULL + st), stageB);
-                    bulk_g2s(smem_u32(smB + st * stageB), wsrc + (size_t)j * stageB, stageB, BAR(B_FULL + st));
+                int ce = chunk_rotation(b, q0);
+                for (int c = 0; c < nchunks && ok; ++c) {
+                    const unsigned char* wc = wsrc + (size_t)ce * K * stageB;
+                    for (int k = 0; k < K && ok; ++k, ++gi) {
+                        const int st = gi % NB2;
+                        if (gi >= NB2) ok = mbar_wait(BAR(B_EMPTY + st), ((gi / NB2) - 1) & 1, a.err);
+                        if (!ok) break;
+                        mbar_expect_tx(BAR(B_FULL + st), stageB);
+                        bulk_g2s(smem_u32(smB + st * stageB), wc + (size_t)k * stageB, stageB, BAR(B_FULL + st));
+                    }
+                    if (++ce == nchunks) ce = 0;
                 }
             }
         }

@@ -21,8 +21,17 @@ struct Hifigan {
     int out_len(int T) const;
     // peak_bits (nullable): device word that conv_post's store folds max|wav| into (atomicMax on the float's bits; the
     // caller zeroes it) -- the first half of save_wav's peak normalisation without another pass over the waveform
+    // lens (nullable, device int32 [B]): valid frames per row.  With it, padded frames are neither computed nor read:
+    // every launch stops `need` samples past a row's end, where `need` is the receptive field of the layers that still
+    // follow (worked out in init()), so all samples below lens[b] * prod(upsample_factors) are bit-identical to the dense
+    // call; the rest of the row is zero.
     int forward(const float* x, const float* g, int B, int T, float* wav, void* ws, size_t ws_bytes,
-                cudaStream_t st, unsigned* peak_bits = nullptr) const;
+                cudaStream_t st, unsigned* peak_bits = nullptr, const int* lens = nullptr) const;
+    // per-launch exactness margins (samples at the tensor's own rate), see init()
+    int need_P = 0;
+    std::vector<int> need_OUT, need_U, need_q_ups, rate;
+    std::vector<std::vector<int>> need_T1, need_X;
+    void plan_margins();
 };
 
 struct WaveNet {
@@ -34,7 +43,7 @@ struct WaveNet {
              const float* const* w, int* consumed);
     size_t scratch_floats(int B, int T) const;
     int forward(float* h, float* out, const float* mask, const float* g, int B, int T, float* acts, float* condv,
-                cudaStream_t st) const;
+                cudaStream_t st, const int* lens = nullptr) const;
 };
 
 struct Flow {
@@ -45,8 +54,11 @@ struct Flow {
     ~Flow();
     int init(const b200tts_flow_config& cfg, const float* const* w, int nw, int forward_direction = 0);
     size_t workspace_bytes(int B, int T) const;
+    // lens (nullable, device int32 [B]): frames per row; rows are neither computed nor read past their length (every
+    // tensor in the flow is re-masked, so the frames below lens[b] are bit-identical to the dense call; z keeps its
+    // input values beyond a row's end instead of the zeros the masking would write -- callers mask z afterwards)
     int reverse(float* z, const float* mask, const float* g, int B, int T, void* ws, size_t ws_bytes,
-                cudaStream_t st) const;
+                cudaStream_t st, const int* lens = nullptr) const;
 };
 
 struct PosteriorEnc {

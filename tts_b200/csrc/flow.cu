@@ -51,7 +51,7 @@ size_t WaveNet::scratch_floats(int B, int T) const {
 
 // h [B,H,T] (masked, updated in place), out [B,H,T] <- WN(h) * mask
 int WaveNet::forward(float* h, float* out, const float* mask, const float* g, int B, int T, float* acts,
-                     float* condv, cudaStream_t st) const {
+                     float* condv, cudaStream_t st, const int* lens) const {
     int rc;
     const long long bs = (long long)H * T;
     const bool has_g = cond_ch > 0 && g != nullptr;
@@ -67,12 +67,14 @@ int WaveNet::forward(float* h, float* out, const float* mask, const float* g, in
             io.x = h; io.x_bs = bs; io.x_cs = T; io.Tin = T;
             io.y = acts; io.y_bs = bs; io.y_cs = T; io.Tout = T; io.B = B;
             io.flags = EPI_GATE;
+            io.lens = lens;      // everything in the WaveNet is re-masked: rows end exactly at their length (need = 0)
             if (has_g) { io.cond = condv + (size_t)l * 2 * H; io.cond_bs = cond.RowsPad; }
             if ((rc = launch_conv(in_layers[l], io, st))) return rc;
         }
         ConvIO io;
         io.x = acts; io.x_bs = bs; io.x_cs = T; io.Tin = T; io.Tout = T; io.B = B;
         io.ymask = mask; io.ymask_bs = T;
+        io.lens = lens;
         if (l < L - 1) {  // h = (h + rs[:H]) * mask ; out (+)= rs[H:]
             io.y = h; io.y_bs = bs; io.y_cs = T;
             io.y2 = out; io.y2_bs = bs; io.y2_cs = T; io.split = H;
@@ -130,7 +132,7 @@ size_t Flow::workspace_bytes(int B, int T) const {
 }
 
 int Flow::reverse(float* z, const float* mask, const float* g, int B, int T, void* ws, size_t ws_bytes,
-                  cudaStream_t st) const {
+                  cudaStream_t st, const int* lens) const {
     B200_REQUIRE(z && mask && ws, "flow_reverse: null pointer");
     // (also runs the forward direction when the handle was packed for it: same kernels, opposite block order,
     //  x1 = m + x1*mask instead of x1 = (x1 - m)*mask)
@@ -158,9 +160,10 @@ int Flow::reverse(float* z, const float* mask, const float* g, int B, int T, voi
             io.x = x0; io.x_bs = zbs; io.x_cs = T; io.Tin = T;
             io.y = h; io.y_bs = (long long)H * T; io.y_cs = T; io.Tout = T; io.B = B;
             io.ymask = mask; io.ymask_bs = T; io.flags = EPI_MASK_POST;
+            io.lens = lens;
             if ((rc = launch_conv(b.pre, io, st))) return rc;
         }
-        if ((rc = b.wn.forward(h, out, mask, g, B, T, acts, condv, st))) return rc;
+        if ((rc = b.wn.forward(h, out, mask, g, B, T, acts, condv, st, lens))) return rc;
         {   // m = post(out) * mask ; x1 = (x1 - m) * mask     (mean_only: log_scale = 0)
             ConvIO io;
             io.x = out; io.x_bs = (long long)H * T; io.x_cs = T; io.Tin = T;
@@ -168,6 +171,7 @@ int Flow::reverse(float* z, const float* mask, const float* g, int B, int T, voi
             io.ymask = mask; io.ymask_bs = T;
             io.scale = fwd ? 1.f : -1.f;   // forward: x1 = m + x1*mask ; reverse: x1 = (x1 - m)*mask
             io.flags = EPI_MASK_PRE | EPI_ACCUM | EPI_MASK_POST;
+            io.lens = lens;
             if ((rc = launch_conv(b.post, io, st))) return rc;
         }
     }
@@ -229,7 +233,7 @@ int PosteriorEnc::forward(const float* x, const float* mask, const float* g, con
         io.ymask = mask; io.ymask_bs = T; io.flags = EPI_MASK_POST;
         if ((rc = launch_conv(pre, io, st))) return rc;
     }
-    if ((rc = wn.forward(h, out, mask, g, B, T, acts, condv, st))) return rc;
+    if ((rc = wn.forward(h, out, mask, g, B, T, acts, condv, st, nullptr))) return rc;
     {
         ConvIO io;
         io.x = out; io.x_bs = (long long)H * T; io.x_cs = T; io.Tin = T;

@@ -68,7 +68,47 @@ int Hifigan::init(const b200tts_hifigan_config& cfg, const float* const* w, int 
     for (auto& l : ups) l.allow_tc = true;
     for (auto& v : rb_c1) for (auto& l : v) l.allow_tc = true;
     for (auto& v : rb_c2) for (auto& l : v) l.allow_tc = true;
+    if (rc == 0) plan_margins();
     return rc;
+}
+
+// Ragged batches: how far past a row's last valid sample must each tensor be exact so that the waveform below the
+// row's end is bit-identical to the dense computation?  Walk the schedule backwards adding each layer's one-sided reach.
+void Hifigan::plan_margins() {
+    const int S = c.num_upsamples, nk = c.num_kernels, nd = c.num_dilations;
+    const bool type1 = c.resblock_type == 1;
+    need_OUT.assign(S, 0); need_U.assign(S, 0); need_q_ups.assign(S, 0); rate.assign(S, 1);
+    need_T1.assign(S * nk, std::vector<int>(nd, 0));
+    need_X.assign(S * nk, std::vector<int>(nd, 0));
+    int r = 1;
+    for (int s = 0; s < S; ++s) { r *= c.upsample_factors[s]; rate[s] = r; }
+    int need_next = std::max(conv_post.pad, conv_post.K - 1 - conv_post.pad);     // what conv_post reads past a sample
+    for (int s = S - 1; s >= 0; --s) {
+        need_OUT[s] = need_next;
+        int worst = 0;
+        for (int j = 0; j < nk; ++j) {
+            int cur = need_OUT[s];
+            for (int n = nd - 1; n >= 0; --n) {
+                const ConvLayer& c1 = rb_c1[s * nk + j][n];
+                const int r1 = std::max(c1.pad, (c1.K - 1) * c1.dil - c1.pad);
+                need_X[s * nk + j][n] = cur;                       // output of this dilation step (R, or OUT for the last)
+                if (type1) {
+                    const ConvLayer& c2 = rb_c2[s * nk + j][n];
+                    const int r2 = std::max(c2.pad, (c2.K - 1) * c2.dil - c2.pad);
+                    need_T1[s * nk + j][n] = cur + r2;
+                    cur += r2 + r1;
+                } else {
+                    cur += r1;
+                }
+            }
+            worst = std::max(worst, cur);
+        }
+        need_U[s] = worst;
+        const ConvLayer& u = ups[s];                               // polyphase: GEMM columns are input steps
+        need_q_ups[s] = (need_U[s] + u.ups - 1) / u.ups;
+        need_next = need_q_ups[s] + std::max(u.pad, (u.K - 1) * u.dil - u.pad);
+    }
+    need_P = need_next;
 }
 
 void Hifigan::stage_dims(int T, std::vector<int>& C, std::vector<int>& L) const {
@@ -103,7 +143,7 @@ int Hifigan::out_len(int T) const {
 }
 
 int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, void* ws, size_t ws_bytes,
-                     cudaStream_t st, unsigned* peak_bits) const {
+                     cudaStream_t st, unsigned* peak_bits, const int* lens) const {
     B200_REQUIRE(x && wav && ws, "hifigan_forward: null pointer");
     B200_REQUIRE((c.cond_channels > 0) == (g != nullptr) || c.cond_channels == 0,
                  "hifigan_forward: model has cond_channels=%d but g is null", c.cond_channels);
@@ -148,6 +188,7 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
         io.x = xin0; io.x_bs = (long long)c.in_channels * x_pitch; io.x_cs = x_pitch; io.Tin = T;
         io.y = P; io.y_bs = (long long)C0 * Tp; io.y_cs = Tp; io.Tout = T; io.B = B;
         if (has_cond) { io.cond = condv; io.cond_bs = cond.RowsPad; }
+        io.lens = lens; io.rate_out = 1; io.need_out = need_P; io.rate_in = 1; io.need_in = T;   // z is defined everywhere
         if ((rc = launch_conv(conv_pre, io, st))) return rc;
     }
     const float* cur = P;
@@ -160,12 +201,15 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
             ConvIO io;
             io.x = cur; io.x_bs = (long long)curC * curPitch; io.x_cs = curPitch; io.Tin = curL; io.in_slope = 0.1f;
             io.y = U; io.y_bs = bs; io.y_cs = Ls; io.Tout = Ls; io.B = B;
+            io.lens = lens; io.rate_in = (s == 0) ? 1 : rate[s - 1]; io.need_in = (s == 0) ? need_P : need_OUT[s - 1];
+            io.rate_out = io.rate_in; io.need_out = need_q_ups[s];      // tiles run over GEMM columns = input steps
             if ((rc = launch_conv(ups[s], io, st))) return rc;
         }
         for (int j = 0; j < c.num_kernels; ++j) {
             const auto& c1 = rb_c1[s * c.num_kernels + j];
             const auto& c2 = rb_c2[s * c.num_kernels + j];
             const float* xin = U;
+            int need_xin = need_U[s];
             float* pp[2] = {R, T1};  // ping-pong for ResBlock2
             for (int n = 0; n < c.num_dilations; ++n) {
                 const bool last = (n == c.num_dilations - 1);
@@ -175,6 +219,8 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
                     ConvIO io;
                     io.x = xin; io.x_bs = bs; io.x_cs = Ls; io.Tin = Ls; io.in_slope = 0.1f;
                     io.y = T1; io.y_bs = bs; io.y_cs = Ls; io.Tout = Ls; io.B = B;
+                    io.lens = lens; io.rate_in = io.rate_out = rate[s];
+                    io.need_in = need_xin; io.need_out = need_T1[s * c.num_kernels + j][n];
                     if ((rc = launch_conv(c1[n], io, st))) return rc;
                     convin = T1;
                     lastconv = &c2[n];
@@ -192,8 +238,12 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
                     dst = type1 ? R : pp[n & 1];
                 }
                 io.y = dst;
+                io.lens = lens; io.rate_in = io.rate_out = rate[s];
+                io.need_in = type1 ? need_T1[s * c.num_kernels + j][n] : need_xin;
+                io.need_out = need_X[s * c.num_kernels + j][n];
                 if ((rc = launch_conv(*lastconv, io, st))) return rc;
                 xin = dst;
+                need_xin = io.need_out;
             }
         }
         cur = OUT;
@@ -209,6 +259,10 @@ int Hifigan::forward(const float* x, const float* g, int B, int T, float* wav, v
         io.y = wav; io.y_bs = (long long)c.out_channels * curL; io.y_cs = curL; io.Tout = curL; io.B = B;
         io.act = ACT_TANH;
         io.peak_bits = peak_bits;
+        io.lens = lens; io.rate_in = io.rate_out = rate.empty() ? 1 : rate.back(); io.need_in = need_OUT.empty() ? 0 : need_OUT.back();
+        io.need_out = 0;
+        if (lens)   // rows may end before any tile of conv_post's fallback kernels writes them: the tail must be zero
+            B200_CUDA_OK(cudaMemsetAsync(wav, 0, (size_t)B * c.out_channels * curL * sizeof(float), st));
         if ((rc = launch_conv(conv_post, io, st))) return rc;
     }
     return 0;

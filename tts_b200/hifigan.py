@@ -175,10 +175,13 @@ class HifiganGenerator(nn.Module):
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
-    def forward(self, x, g=None, peak=None):
+    def forward(self, x, g=None, peak=None, lengths=None):
         """x [B, C, T] (CUDA), g [B, cond, 1] -> waveform [B, out_channels, T*prod(upsample_factors)]
         (hifigan_generator.py:236-265).  ``peak`` (optional int32[1] device word, zeroed by the caller): conv_post folds
-        max|wav| into it while storing -- the first half of save_wav's peak normalisation (tts_b200.vocoder.wav_to_int16)."""
+        max|wav| into it while storing -- the first half of save_wav's peak normalisation (tts_b200.vocoder.wav_to_int16).
+        ``lengths`` (optional [B] valid frames per row of a padded batch): padded frames are neither computed nor read;
+        samples below ``lengths[b] * prod(upsample_factors)`` are bit-identical to the dense call, the rest of the row is
+        zero (the dense call -- like the reference -- fills it with the network's response to zero input)."""
         _lib.require_cuda(x, "x")
         if hasattr(self, "cond_layer") and g is None:
             raise ValueError("tts_b200.HifiganGenerator: model has a cond_layer but g is None")
@@ -196,12 +199,14 @@ class HifiganGenerator(nn.Module):
             wav = torch.empty((b, self._cfg["out_channels"], tout), dtype=torch.float32, device=x.device)
             nbytes = L.b200tts_hifigan_workspace_bytes(h, b, t)
             ws = _lib.workspace(x.device, nbytes, "hifigan")
-            if peak is None:
+            if peak is None and lengths is None:
                 rc = L.b200tts_hifigan_forward(h, _lib.ptr(x), _lib.ptr(gl), b, t, _lib.ptr(wav), _lib.ptr(ws),
                                                ctypes.c_size_t(ws.numel()), _lib.stream_ptr(x.device))
             else:
-                rc = L.b200tts_hifigan_forward_peak(h, _lib.ptr(x), _lib.ptr(gl), b, t, _lib.ptr(wav), _lib.ptr(peak),
-                                                    _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr(x.device))
+                lens = None if lengths is None else lengths.to(device=x.device, dtype=torch.int32).contiguous()
+                rc = L.b200tts_hifigan_forward_ex(h, _lib.ptr(x), _lib.ptr(gl), b, t, _lib.ptr(wav), _lib.ptr(lens),
+                                                  _lib.ptr(peak), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                                  _lib.stream_ptr(x.device))
         _lib.check(rc, "hifigan_forward")
         return wav
 

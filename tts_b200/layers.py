@@ -197,8 +197,11 @@ class ResidualCouplingBlocks(EngineModule):
         return self._handle_fwd
 
     @torch.no_grad()
-    def forward(self, x, x_mask, g=None, reverse=False):
+    def forward(self, x, x_mask, g=None, reverse=False, lengths=None):
         """x [B,C,T], x_mask [B,1,T], g [B,cond,1] -> z [B,C,T]   (networks.py:214-232).
+        ``lengths`` (optional int [B] = the row sums of x_mask): padded frames are neither computed nor read; frames
+        below a row's length are bit-identical to the dense call and the result is masked (zero) beyond it, as the
+        reference's per-layer masking leaves it.
         reverse=True is the synthesis direction; reverse=False the posterior->prior direction used by voice
         conversion (the per-block log-determinant the reference discards at :226 is not computed)."""
         _lib.require_cuda(x, "x")
@@ -217,9 +220,16 @@ class ResidualCouplingBlocks(EngineModule):
         L = _lib.lib()
         with torch.cuda.device(z.device):
             ws = _lib.workspace(z.device, L.b200tts_flow_workspace_bytes(h, b, t), "flow")
-            rc = L.b200tts_flow_reverse(h, _lib.ptr(z), _lib.ptr(mask), _lib.ptr(gl), b, t, _lib.ptr(ws),
-                                        ctypes.c_size_t(ws.numel()), _lib.stream_ptr(z.device))
+            if lengths is None:
+                rc = L.b200tts_flow_reverse(h, _lib.ptr(z), _lib.ptr(mask), _lib.ptr(gl), b, t, _lib.ptr(ws),
+                                            ctypes.c_size_t(ws.numel()), _lib.stream_ptr(z.device))
+            else:
+                lens = lengths.to(device=z.device, dtype=torch.int32).contiguous()
+                rc = L.b200tts_flow_reverse_ragged(h, _lib.ptr(z), _lib.ptr(mask), _lib.ptr(gl), _lib.ptr(lens), b, t,
+                                                   _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr(z.device))
         _lib.check(rc, "flow_reverse" if reverse else "flow_forward")
+        if lengths is not None:
+            z = z * mask         # rows keep their input values past their end in the ragged schedule: the reference has zeros
         if self.num_flows % 2:  # the channel flips are folded into the packed weights; an odd count leaves one over
             z = torch.flip(z, [1])
         return z if t == t_in else z[:, :, :t_in].contiguous()

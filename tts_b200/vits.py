@@ -179,6 +179,10 @@ class Vits(nn.Module):
         self.noise_scale_dp = a.noise_scale_dp
         self.max_inference_len = a.max_inference_len
         self.spec_segment_size = a.spec_segment_size
+        # tts_b200 extension (default off = the reference's batch semantics, padded tail included): skip the padded frames
+        # of a batch in the flow and the decoder.  Every sample below ``wav_lengths[b]`` stays bit-identical; the padded
+        # tail of ``model_outputs`` (the decoder's response to zero input, which no caller keeps) becomes zero.
+        self.trim_padding = False
         if a.encoder_sample_rate:   # vits.py:809-810 (the training-only torchaudio resampler is not needed here)
             self.interpolate_factor = _get(config, "audio")["sample_rate"] / a.encoder_sample_rate
 
@@ -345,8 +349,9 @@ class Vits(nn.Module):
                                                           float(self.inference_noise_scale), t_dec,
                                                           want_attn=return_alignments)
         frame_lengths = y_lengths            # valid decoder frames per utterance at the decoder's input rate
+        ragged = bool(getattr(self, "trim_padding", False)) and x.shape[0] > 1
         with _Stage(self, "flow"):
-            z = self.flow(z_p, y_mask, g=g, reverse=True)
+            z = self.flow(z_p, y_mask, g=g, reverse=True, lengths=y_lengths if ragged else None)
             if a.encoder_sample_rate and a.interpolate_z:   # upsampling_z, vits.py:944-959
                 f = self.interpolate_factor
                 z = upsample_linear(z, f)
@@ -361,7 +366,7 @@ class Vits(nn.Module):
                 zin = zin[:, :, : self.max_inference_len]
                 frame_lengths = torch.clamp_max(frame_lengths, int(self.max_inference_len))
         with _Stage(self, "waveform_decoder"):
-            o = self.waveform_decoder(zin, g=g)
+            o = self.waveform_decoder(zin, g=g, lengths=frame_lengths if ragged else None)
         hop = o.shape[-1] // max(zin.shape[-1], 1)      # prod(upsample_rates_decoder)
         # the reference's eight keys (vits.py:1163-1172) plus: y_lengths (frames at the text-side rate), logw, and
         # wav_lengths = valid output samples per utterance (after latent upsampling / max_inference_len cropping)
