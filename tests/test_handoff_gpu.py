@@ -94,3 +94,48 @@ def test_product_matches_the_real_reference_model_fixture(golden):
     err = out["model_outputs"].cpu() - want["model_outputs"]
     rms, ref = float(err.pow(2).mean().sqrt()), float(want["model_outputs"].pow(2).mean().sqrt())
     assert rms <= 1e-4 and rms <= 1e-4 * ref, (rms, ref)
+
+
+def test_synthesize_batched_on_device_vs_sentence_at_a_time_oracle():
+    """what Synthesizer.tts does one sentence per call (synthesizer.py:384-441), as three length buckets
+    on the device.  Per sentence: durations / alignment bit-exact vs the oracle's batch-1 inference; waveform equal up
+    to the decoder's receptive field before the sentence's end (there a padded row differs from a solo run in the
+    reference too); then the joined int16 stream equals save_wav's arithmetic on the same float samples."""
+    from dataclasses import asdict
+
+    import numpy as np
+
+    import vits_oracle as O
+    from tts_b200.parallel import concat_sentences, synthesize_batched, synthesize_to_int16
+    from tts_b200.vits import Vits, VitsArgs, VitsConfig
+    torch.manual_seed(31)
+    args = VitsArgs(upsample_initial_channel_decoder=64, num_layers_text_encoder=2, hidden_channels_ffn_text_encoder=256)
+    m = Vits(VitsConfig(model_args=args)).eval()
+    gen = torch.Generator().manual_seed(32)
+    for _, p in m.named_parameters():
+        if float(p.detach().abs().sum()) == 0.0:
+            p.data.copy_(torch.randn(p.shape, generator=gen) * 0.05)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.cuda()
+    lens = [23, 7, 40, 22, 8, 39, 3]
+    seqs = [torch.randint(1, 100, (n,), generator=gen).tolist() for n in lens]
+    sdp = [torch.randn(2, n, generator=gen) for n in lens]
+    prior = lambda i, c, t: torch.randn(c, t, generator=torch.Generator().manual_seed(1000 + i))
+    got = synthesize_batched(m, seqs, max_padded_tokens=96, max_batch=3, sdp_noise=sdp, prior_noise=prior)
+    from tts_b200.parallel import bucket_by_length
+    assert len(bucket_by_length(lens, 96, 3)) >= 3
+    a = asdict(args)
+    for i, s in enumerate(seqs):
+        want = O.vits_inference(sd, torch.tensor([s]), torch.tensor([len(s)]), sdp[i].unsqueeze(0),
+                                lambda shape, i=i: prior(i, shape[1], shape[2]).unsqueeze(0), args=a)
+        n = int(want["y_lengths"][0]) * 256
+        assert got[i].shape == (n,), (i, got[i].shape, n)
+        keep = max(0, n - 16 * 256)                         # 16 frames > the decoder's reach past a sentence's end
+        err = got[i][:keep].cpu() - want["model_outputs"][0, 0, :keep]
+        ref = want["model_outputs"][0, 0, :keep]
+        if keep:
+            assert float(err.pow(2).mean().sqrt()) <= 1e-4 * max(float(ref.pow(2).mean().sqrt()), 1e-6), i
+    joined = concat_sentences(got, gap=10000)
+    want16 = O.wav_to_int16(joined.cpu().numpy())
+    got16 = synthesize_to_int16(m, seqs, max_padded_tokens=96, max_batch=3, sdp_noise=sdp, prior_noise=prior)
+    assert got16.dtype == torch.int16 and np.array_equal(got16.cpu().numpy(), want16)

@@ -561,18 +561,20 @@ __global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restric
                                                           const float* __restrict__ bias, float slope, int act,
                                                           float* __restrict__ y, long long y_bs,
                                                           unsigned* __restrict__ peak_bits, const int* __restrict__ lens,
-                                                          int rate, int need) {
+                                                          int rate, int need_out, int need_in) {
     constexpr int PAD = (K - 1) / 2, NL = (4 + 4 + (K - 1 - PAD) + 3) / 4;   // float4 loads covering [t0 - 4, t0 + 4 + K-1-PAD)
     extern __shared__ float ws[];
     for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) ws[i] = w[(size_t)i * w_stride];
     __syncthreads();
     const int b = blockIdx.y;
-    // ragged batch: row b holds data below Tb only (a multiple of 4); samples from Tb on are written as zeros and the
-    // input is read as zero there -- so the padded tail of the waveform is clean and costs no bandwidth
-    int Tb = T;
+    // ragged batch: row b is computed below Tb only (a multiple of 4) and samples from Tb on are written as zeros, so the
+    // padded tail of the waveform is clean; the input holds data below Ti (its producer's extent) and reads as zero beyond
+    int Tb = T, Ti = T;
     if (lens) {
-        const long long e = ((long long)lens[b] * rate + need + 3) / 4 * 4;
+        const long long base = (long long)lens[b] * rate;
+        const long long e = (base + need_out + 3) / 4 * 4, ei = (base + need_in + 3) / 4 * 4;
         Tb = (int)(e < (long long)T ? (e > 0 ? e : 0) : (long long)T);
+        Ti = (int)(ei < (long long)T ? (ei > 0 ? ei : 0) : (long long)T);
     }
     if ((int)(blockIdx.x * blockDim.x) * 4 >= Tb && !peak_bits) {        // whole block beyond the row: zero fill and leave
         const int tz = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(256) conv1d_row1_kernel(const float* __restric
             for (int l = 0; l < NL; ++l) {
                 const int t = t0 - 4 + 4 * l;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= 0 && t < Tb) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // Tb % 4 == 0: all in or all out
+                if (t >= 0 && t < Ti) v = __ldg(reinterpret_cast<const float4*>(xr - 4 + 4 * l));   // Ti % 4 == 0: all in or all out
                 win[4 * l] = v.x; win[4 * l + 1] = v.y; win[4 * l + 2] = v.z; win[4 * l + 3] = v.w;
             }
 #pragma unroll
@@ -927,7 +929,7 @@ int launch_conv(const ConvLayer& L, const ConvIO& io, cudaStream_t st) {
                 conv1d_row1_kernel<7><<<grid, 256, (size_t)L.Cin * L.K * 4, st>>>(a.x, a.x_bs, a.x_cs, L.Cin, a.Tout, L.w,
                                                                                  L.co_tile, L.bias, a.in_slope, a.act, a.y,
                                                                                  a.y_bs, io.peak_bits, a.lens, a.rate_out,
-                                                                                 a.need_out);
+                                                                                 a.need_out, a.need_in);
                 count_launch();
                 dispatch_note(DISPATCH_ROW1);
                 B200_CUDA_OK(cudaGetLastError());

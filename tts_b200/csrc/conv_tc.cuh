@@ -78,6 +78,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
     if (err) { *reinterpret_cast<volatile int*>(err) = 1; __threadfence_system(); }   // mapped host flag (conv1d.cu)
     return false;
 }
+// non-blocking probe of a phase (mbarrier.test_wait: returns at once, unlike try_wait which may suspend the thread)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

@@ -209,14 +209,6 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         b = rest / a.n_rtiles;
         q0 = tt * a.tstep;
     };
-    // Every CTA of the grid walks the SAME weight tensor; in lock step they would all ask the L2 for the same 8 KB block
-    // at the same time (measured: the few slices holding it saturate while 5/6 of the L2 idles, ~17 B/clk per SM).
-    // Each TILE therefore starts its channel-chunk loop at its own offset -- a function of the tile's coordinates only,
-    // so an output element is always accumulated in the same order whatever the schedule (dense / ragged / grid size).
-    auto chunk_rotation = [&](int b, int q0) -> int {
-        if (a.dbg & 32) return 0;
-        return (int)((unsigned)(b * 5 + q0 / a.tstep) % (unsigned)nchunks);
-    };
     auto input_extent = [&](int b) -> int {       // columns of x[b] that hold data; beyond it the operand is zero
         if (!ragged) return a.Tin;
         const long long e = (long long)a.lens[b] * a.rate_in + a.need_in;
@@ -250,7 +242,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             i_raw[e] = (idx < 2 * ROWS) ? (4 * sl) * RAWW + r : -1;
             i_dst[e] = (int)(sl * slabA) + r * 16;
         }
-        int iss_it = -1, iss_b = 0, iss_q0 = 0, iss_Tin = 0, iss_rot = 0;   // the tile the cp.async front is in (decoded once per tile)
+        int iss_it = -1, iss_b = 0, iss_q0 = 0, iss_Tin = 0;   // the tile the cp.async front is in (decoded once per tile)
         int tr_it = -1, tr_q0 = 0;                                // the tile the transform is in
         auto issue = [&](int g) {
             if (g < total && !(a.dbg & 1)) {
@@ -259,12 +251,9 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                     int rt_;
                     decode(it, iss_b, rt_, iss_q0);
                     iss_Tin = input_extent(iss_b);
-                    iss_rot = chunk_rotation(iss_b, iss_q0);
                     iss_it = it;
                 }
                 const int b = iss_b, q0 = iss_q0, Tin_b = iss_Tin;
-                int ce = c + iss_rot;                                     // this tile's channel-chunk order (see chunk_rotation)
-                if (ce >= nchunks) ce -= nchunks;
                 const int tal = ((q0 - a.pad) & ~3);                     // 16-byte aligned window start (may be < 0)
                 const float* xb = a.x + (long long)b * a.x_bs;
                 const uint32_t dst0 = smem_u32(smRaw + (g % NRAW) * rawStage);
@@ -272,7 +261,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 for (int e = 0; e < MAXV; ++e) {
                     if (v_ch[e] < 0) continue;
                     const int t = tal + v_t[e];
-                    const int cg = ce * KC2 + v_ch[e];
+                    const int cg = c * KC2 + v_ch[e];
                     // t is a multiple of 4, so a vector is either wholly before the sequence start (zero fill),
                     // wholly inside, or cut by its end (partial source size, rest zero-filled by the hardware)
                     int nb = 0;
@@ -344,63 +333,86 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 int b, rt, q0;
                 decode(it, b, rt, q0);
                 const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.w) + (size_t)rt * total * stageB;
-                int ce = chunk_rotation(b, q0);
-                for (int c = 0; c < nchunks && ok; ++c) {
-                    const unsigned char* wc = wsrc + (size_t)ce * K * stageB;
-                    for (int k = 0; k < K && ok; ++k, ++gi) {
-                        const int st = gi % NB2;
-                        if (gi >= NB2) ok = mbar_wait(BAR(B_EMPTY + st), ((gi / NB2) - 1) & 1, a.err);
-                        if (!ok) break;
-                        mbar_expect_tx(BAR(B_FULL + st), stageB);
-                        bulk_g2s(smem_u32(smB + st * stageB), wc + (size_t)k * stageB, stageB, BAR(B_FULL + st));
-                    }
-                    if (++ce == nchunks) ce = 0;
+                for (int j = 0; j < total && ok; ++j, ++gi) {
+                    const int st = gi % NB2;
+                    if (gi >= NB2) ok = mbar_wait(BAR(B_EMPTY + st), ((gi / NB2) - 1) & 1, a.err);
+                    if (!ok) break;
+                    mbar_expect_tx(BAR(B_FULL + st), stageB);
+                    bulk_g2s(smem_u32(smB + st * stageB), wsrc + (size_t)j * stageB, stageB, BAR(B_FULL + st));
                 }
             }
         }
     } else if (warp == 9) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        // ncu (profiles/r02_tc3_issue_loop.md): this ONE thread is what bounds the MMA-heavy layers -- it never waits long
+        // on a barrier, its own dependent instruction chain took ~710 cycles per tap against the 384 cycles the three MMAs
+        // need on the tensor pipe.  So the loop carries no divisions / modulos / constant-bank loads / descriptor
+        // rebuilds: ring positions, parities, barrier addresses and descriptors are running counters, and the next tap's
+        // weight barrier is tested (non-blocking) BEFORE the current tap's MMAs are issued so its latency is off the chain.
+        // The whole warp runs the loop CONVERGED (every lane computes the same ring positions / descriptors, so the
+        // compiler keeps them in uniform registers and feeds UTCHMMA directly -- inside an `if (lane == 0)` every operand
+        // went through R2UR and each tcgen05 instruction got its own ELECT loop); one elected lane issues.
+        {
+            uint32_t leader;
+            asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
             // M = 128 rows (weights), N = 256 time steps
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TT2 >> 3) << 17) | ((uint32_t)(MROWS >> 4) << 24);
+            const uint64_t xstep = (uint64_t)a.dil_blk;                                   // B rows per tap (16 B each)
+            const uint64_t wlo_off = (uint64_t)((2 * slabB) >> 4), wslot = (uint64_t)(stageB >> 4);
+            const uint64_t wdesc0 = make_desc(smem_u32(smB), slabB);
+            const uint32_t bfull0 = BAR(B_FULL), bempty0 = BAR(B_EMPTY);
+            const bool no_mma = (a.dbg & 16) != 0;
             bool ok = true;
-            int g = 0, gi = 0;
+            int sa = 0; uint32_t pa = 0;                                                  // activation stage / its parity
+            int sb = 0; uint32_t pb = 0;                                                  // weight slot / its parity
+            uint64_t wdesc = wdesc0;
+            uint32_t bfull = bfull0, bempty = bempty0;
+            bool have = false;                                                            // B_FULL[sb] already seen complete
             for (int it = 0; it < my_tiles && ok; ++it) {
                 const int buf = it & 1;
                 if (it >= 2) ok = mbar_wait(BAR(ACC_EMPTY + buf), ((it >> 1) - 1) & 1, a.err);
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + (uint32_t)buf * acc_cols;
-                for (int c = 0; c < nchunks && ok; ++c, ++g) {
-                    const int sa = g % NA2;
-                    ok = mbar_wait(BAR(A_FULL + sa), (g / NA2) & 1, a.err);
+                uint32_t acc = 0u;
+                for (int c = 0; c < nchunks && ok; ++c) {
+                    ok = mbar_wait(BAR(A_FULL + sa), pa, a.err);
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t abase = smem_u32(smA + sa * stageA);
                     // descriptors differ only in the 14-bit start-address field: build once, then add rows (16 B each)
-                    const uint64_t x_hi0 = make_desc(abase, slabA), x_lo0 = make_desc(abase + 2 * slabA, slabA);
-                    for (int k = 0; k < K && ok; ++k, ++gi) {
-                        const int sb = gi % NB2;
-                        ok = mbar_wait(BAR(B_FULL + sb), (gi / NB2) & 1, a.err);
-                        if (!ok) break;
+                    uint64_t xh = make_desc(abase, slabA), xl = make_desc(abase + 2 * slabA, slabA);
+#pragma unroll 1
+                    for (int k = 0; k < K; ++k) {
+                        if (!have) { ok = mbar_wait(bfull, pb, a.err); if (!ok) break; }
                         tc_fence_after();
-                        const uint32_t bbase = smem_u32(smB + sb * stageB);
-                        const uint64_t w_hi = make_desc(bbase, slabB);
-                        const uint64_t w_lo = w_hi + (uint64_t)((2 * slabB) >> 4);
-                        const uint64_t xrow = (uint64_t)(k * a.dil_blk);
-                        if (!(a.dbg & 16)) {
-                        mma_tf32(dcol, w_hi, x_lo0 + xrow, idesc, (c == 0 && k == 0) ? 0u : 1u);   // small terms first
-                        mma_tf32(dcol, w_lo, x_hi0 + xrow, idesc, 1u);
-                        mma_tf32(dcol, w_hi, x_hi0 + xrow, idesc, 1u);
+                        // where the NEXT tap's weights will be; peek at their barrier now (result used next iteration)
+                        const bool wrap = (sb == NB2 - 1);
+                        const uint32_t nfull = wrap ? bfull0 : bfull + 8u, npb = wrap ? (pb ^ 1u) : pb;
+                        const bool have_next = mbar_test(nfull, npb);
+                        const uint64_t w_hi = wdesc, w_lo = wdesc + wlo_off;
+                        if (leader) {
+                            if (!no_mma) {
+                                mma_tf32(dcol, w_hi, xl, idesc, acc);                     // small terms first
+                                mma_tf32(dcol, w_lo, xh, idesc, 1u);
+                                mma_tf32(dcol, w_hi, xh, idesc, 1u);
+                            }
+                            mma_commit(bempty);
                         }
-                        mma_commit(BAR(B_EMPTY + sb));
+                        acc = 1u;
+                        xh += xstep; xl += xstep;
+                        if (wrap) { sb = 0; wdesc = wdesc0; bempty = bempty0; }
+                        else { ++sb; wdesc += wslot; bempty += 8u; }
+                        bfull = nfull; pb = npb;
+                        have = __all_sync(0xffffffffu, have_next);                        // keep the warp's control flow uniform
                     }
-                    if (ok) mma_commit(BAR(A_EMPTY + sa));
+                    if (ok && leader) mma_commit(BAR(A_EMPTY + sa));
+                    if (++sa == NA2) { sa = 0; pa ^= 1u; }
                 }
-                if (ok) mma_commit(BAR(ACC_FULL + buf));
-                if (it == 0) TC3_STAMP(8); if (it == 1) TC3_STAMP(9); if (it == 3) TC3_STAMP(10);
+                if (ok && leader) mma_commit(BAR(ACC_FULL + buf));
+                if (lane == 0) { if (it == 0) TC3_STAMP(8); if (it == 1) TC3_STAMP(9); if (it == 3) TC3_STAMP(10); }
             }
-            TC3_STAMP(11);
+            if (lane == 0) TC3_STAMP(11);
         }
         __syncwarp();
     } else {

@@ -18,6 +18,8 @@
 // contraction), evaluated in the reference's order, so paths are bit-identical.  Cells outside
 // the band keep value*mask exactly like the reference's untouched entries, which also makes the
 // degenerate t_x > t_y case follow core.pyx (minus its unused out-of-row read at y == 0).
+#include <stdlib.h>
+
 #include "engines.cuh"
 
 namespace b200tts {
@@ -353,6 +355,165 @@ __global__ void __launch_bounds__(MAS_NT) mas_kernel2(const MasArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ third generation: no CTA barrier in the DP loop
+// mas_kernel2 spends its time in one __syncthreads per DP column (ncu: the barrier is the top stall, issue slots 56 %
+// busy).  The only cross-warp dependency of column y is ONE value: lane 0 of warp w needs stored[32w - 1, y - 1] from
+// lane 31 of warp w - 1.  So the warps run as a skewed wavefront: each publishes that boundary value into a small ring
+// in shared memory with a release store of its progress counter, its right neighbour acquires the counter (cached: it
+// polls only when it has caught up) -- no barrier at all between the first column and the backtrack.
+// Values never touch shared memory either: lane x streams row x as two LDG.128 per 8 columns (full 32-byte sectors),
+// prefetched two groups ahead in registers.
+constexpr int MAS3_RING = 64;          // boundary slots per warp (columns a producer may run ahead of its consumer)
+
+__device__ __forceinline__ int ld_acquire_s32(unsigned addr) { int v; asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void st_release_s32(unsigned addr, int v) { asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(MAS_NT, 3) mas_kernel3(const MasArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Tx = a.Tx, Ty = a.Ty, W = a.W;
+    constexpr int NW = MAS_NT / 32;
+    const int tx = min(max(a.t_x[b], 0), Tx), ty = min(max(a.t_y[b], 0), Ty);
+    int* idxs = reinterpret_cast<int*>(smem_raw);                              // [Ty]
+    unsigned* dirs = reinterpret_cast<unsigned*>(idxs + Ty);                   // [Ty][W]
+    float* ring = reinterpret_cast<float*>(dirs + (size_t)Ty * W);             // [NW][MAS3_RING]
+    int* prog = reinterpret_cast<int*>(ring + NW * MAS3_RING);                 // [NW] columns completed per warp
+    if (tid < NW) prog[tid] = 0;
+    __syncthreads();
+
+    const int x = tid;
+    const bool xin = x < Tx, active = warp < W;
+    if (active && tx > 0 && ty > 0) {
+        const size_t row = ((size_t)b * Tx + (size_t)(xin ? x : Tx - 1)) * Ty;
+        const float4* vrow = reinterpret_cast<const float4*>(a.value + row);
+        const float4* mrow = HAS_MASK ? reinterpret_cast<const float4*>(a.mask + row) : nullptr;
+        const int ngroups = (ty + 7) / 8, Ty4 = Ty >> 2;
+        auto load = [&](int g, float* v) {                 // columns [8g, 8g + 8) of this lane's row (masked on load)
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
+            if (g < ngroups) {
+                p = __ldg(vrow + 2 * g);
+                if (2 * g + 1 < Ty4) q = __ldg(vrow + 2 * g + 1);
+                if (HAS_MASK) {
+                    const float4 mp = __ldg(mrow + 2 * g);
+                    float4 mq = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (2 * g + 1 < Ty4) mq = __ldg(mrow + 2 * g + 1);
+                    p.x = __fmul_rn(p.x, mp.x); p.y = __fmul_rn(p.y, mp.y); p.z = __fmul_rn(p.z, mp.z); p.w = __fmul_rn(p.w, mp.w);
+                    q.x = __fmul_rn(q.x, mq.x); q.y = __fmul_rn(q.y, mq.y); q.z = __fmul_rn(q.z, mq.z); q.w = __fmul_rn(q.w, mq.w);
+                }
+            }
+            v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+        };
+        const bool x_lt_tx = x < tx, is_x0 = (x == 0);
+        const int c1 = x - tx + ty;
+        const float neg = a.max_neg;
+        const bool first = (warp == 0), last = (warp == W - 1);
+        const unsigned a_ring_w = (unsigned)__cvta_generic_to_shared(ring + warp * MAS3_RING);
+        const unsigned a_ring_r = (unsigned)__cvta_generic_to_shared(ring + (first ? 0 : warp - 1) * MAS3_RING);
+        const unsigned a_prog_w = (unsigned)__cvta_generic_to_shared(prog + warp);
+        const unsigned a_prog_l = (unsigned)__cvta_generic_to_shared(prog + (first ? 0 : warp - 1));
+        const unsigned a_prog_r = (unsigned)__cvta_generic_to_shared(prog + (last ? warp : warp + 1));
+        unsigned a_dir = (unsigned)__cvta_generic_to_shared(dirs + warp);
+        int seen_left = 0, seen_right = 0;                // cached progress of the neighbours
+        float vc = 0.f;                                   // stored[x, y - 1]
+        float cur[8], n1[8], n2[8];
+        load(0, cur); load(1, n1); load(2, n2);
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+            float n3[8];
+            load(g + 3, n3);
+            const int ylim = min(8, ty - 8 * g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < ylim) {
+                    const int y = 8 * g + j;
+                    const float raw = xin ? cur[j] : 0.f;
+                    float left = __shfl_up_sync(0xffffffffu, vc, 1);
+                    if (lane == 0 && !first && y > 0) {                 // stored[32w - 1, y - 1] from the left warp
+                        while (seen_left < y) seen_left = ld_acquire_s32(a_prog_l);
+                        left = lds_f32(a_ring_r + (unsigned)((y - 1) & (MAS3_RING - 1)) * 4u);
+                    }
+                    const bool x_eq_y = (x == y);
+                    const bool dir = xin && !is_x0 && (y > 0) && (x_eq_y || vc < left);
+                    const bool inband = x_lt_tx && (x <= y) && (c1 >= y);
+                    const float v_cur = x_eq_y ? neg : vc;
+                    const float v_prev = is_x0 ? (y == 0 ? 0.f : neg) : left;
+                    const float upd = __fadd_rn(fmaxf(v_cur, v_prev), raw);
+                    vc = inband ? upd : raw;
+                    const unsigned word = __ballot_sync(0xffffffffu, dir);
+                    if (lane == 0) sts_u32(a_dir, word);
+                    a_dir += (unsigned)W * 4u;
+                    if (lane == 31) {
+                        if (!last) {
+                            // do not overwrite a slot the right warp has not read yet (it reads column c at its column c + 1)
+                            while (seen_right < y - MAS3_RING + 2) seen_right = ld_acquire_s32(a_prog_r);
+                            sts_f32(a_ring_w + (unsigned)(y & (MAS3_RING - 1)) * 4u, vc);
+                        }
+                        st_release_s32(a_prog_w, y + 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cur[j] = n1[j]; n1[j] = n2[j]; n2[j] = n3[j]; }
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && tx > 0) {
+        int index = tx - 1;
+        for (int ytop = ty - 1; ytop >= 0; ytop -= MAS_DEPTH) {
+            unsigned rows[MAS_DEPTH];
+#pragma unroll
+            for (int d = 0; d < MAS_DEPTH; ++d) {
+                const int y = ytop - d;
+                rows[d] = (y >= 1 && lane < W) ? dirs[(size_t)y * W + lane] : 0u;
+            }
+#pragma unroll
+            for (int d = 0; d < MAS_DEPTH; ++d) {
+                const int y = ytop - d;
+                if (y < 0) break;
+                if (lane == 0) idxs[y] = index;
+                if (y >= 1) {
+                    const unsigned word = __shfl_sync(0xffffffffu, rows[d], index >> 5);
+                    index -= (int)((word >> (index & 31)) & 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const bool valid = tx > 0;
+    const int Ty4 = Ty >> 2;                               // the launcher guarantees Ty % 4 == 0
+    if (a.path_is_f32) {
+        float4* pb4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.path) + (size_t)b * Tx * Ty);
+        for (int xx = warp; xx < Tx; xx += NW)
+            for (int j = lane; j < Ty4; j += 32) {
+                const int y = j << 2;
+                float4 o;
+                o.x = (valid && y + 0 < ty && idxs[y + 0] == xx) ? 1.f : 0.f;
+                o.y = (valid && y + 1 < ty && idxs[y + 1] == xx) ? 1.f : 0.f;
+                o.z = (valid && y + 2 < ty && idxs[y + 2] == xx) ? 1.f : 0.f;
+                o.w = (valid && y + 3 < ty && idxs[y + 3] == xx) ? 1.f : 0.f;
+                pb4[(size_t)xx * Ty4 + j] = o;
+            }
+    } else {
+        int4* pb4 = reinterpret_cast<int4*>(reinterpret_cast<int*>(a.path) + (size_t)b * Tx * Ty);
+        for (int xx = warp; xx < Tx; xx += NW)
+            for (int j = lane; j < Ty4; j += 32) {
+                const int y = j << 2;
+                int4 o;
+                o.x = (valid && y + 0 < ty && idxs[y + 0] == xx) ? 1 : 0;
+                o.y = (valid && y + 1 < ty && idxs[y + 1] == xx) ? 1 : 0;
+                o.z = (valid && y + 2 < ty && idxs[y + 2] == xx) ? 1 : 0;
+                o.w = (valid && y + 3 < ty && idxs[y + 3] == xx) ? 1 : 0;
+                pb4[(size_t)xx * Ty4 + j] = o;
+            }
+    }
+}
+
+static size_t mas3_smem(int Tx, int Ty) {
+    const int W = (Tx + 31) / 32;
+    return (size_t)Ty * 4 + (size_t)Ty * W * 4 + (size_t)(MAS_NT / 32) * MAS3_RING * 4 + (size_t)(MAS_NT / 32) * 4 + 16;
+}
+
 static size_t mas2_smem(int Tx, int Ty, bool has_mask, bool dirs_in_smem) {
     const int TxP = (Tx | 31) + 2, W = (Tx + 31) / 32;
     return (size_t)(has_mask ? 4 : 2) * MAS2_YT * TxP * 4 + 2 * (MAS_NT / 32) * 4 + (size_t)Ty * 4 +
@@ -389,7 +550,30 @@ int mas_forward(const float* value, const float* mask, const int* t_x, const int
     B200_REQUIRE(B >= 0 && Tx >= 0 && Ty >= 0, "mas: negative size");
     if (B == 0 || Tx == 0 || Ty == 0) return 0;
     B200_REQUIRE(value && t_x && t_y && path, "mas: null pointer");
-    static DeviceOnce attr2_once, attr_once;
+    static DeviceOnce attr2_once, attr_once, attr3_once;
+    static int use3 = -1;
+    // measured at cfg4 (r02): 0.63 ms against mas_kernel2's 0.47 ms -- the per-lane row streaming (32 lines per LDG) and
+    // three CTAs per SM cost more than the barriers save.  Kept as an opt-in experiment (B200TTS_MAS3=1), see DESIGN.md.
+    if (use3 < 0) { const char* e = getenv("B200TTS_MAS3"); use3 = (e && atoi(e)) ? 1 : 0; }
+    const bool aligned16 = (Ty % 4 == 0) && ((reinterpret_cast<uintptr_t>(value) & 15) == 0) &&
+                           (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0) && ((reinterpret_cast<uintptr_t>(path) & 15) == 0);
+    if (use3 && Tx <= MAS_NT && aligned16 && mas3_smem(Tx, Ty) <= 200 * 1024) {     // wavefront kernel (no CTA barrier per column)
+        if (int rc = device_once(attr3_once, nullptr, [](int) -> int {
+                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                B200_CUDA_OK(cudaFuncSetAttribute(mas_kernel3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                return 0;
+            })) return rc;
+        MasArgs a3;
+        a3.value = value; a3.mask = mask; a3.t_x = t_x; a3.t_y = t_y;
+        a3.B = B; a3.Tx = Tx; a3.Ty = Ty; a3.YT = 8; a3.W = (Tx + 31) / 32;
+        a3.path = path; a3.path_is_f32 = path_is_f32; a3.dirs_global = nullptr; a3.dirs_in_smem = 1; a3.max_neg = -1e9f;
+        const size_t smem3 = mas3_smem(Tx, Ty);
+        if (mask) mas_kernel3<true><<<B, MAS_NT, smem3, st>>>(a3);
+        else mas_kernel3<false><<<B, MAS_NT, smem3, st>>>(a3);
+        count_launch();
+        B200_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (Tx <= MAS_NT) {     // lean kernel
         bool dsm = mas2_smem(Tx, Ty, mask != nullptr, true) <= 72 * 1024;
         const size_t smem2 = mas2_smem(Tx, Ty, mask != nullptr, dsm);

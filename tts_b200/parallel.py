@@ -190,13 +190,19 @@ def bucket_by_length(lengths: Sequence[int], max_padded_tokens: int = 4096, max_
 
 
 def synthesize_batched(model, token_seqs: Sequence[Sequence[int]], aux_input=None, pad_id: int = 0,
-                       max_padded_tokens: int = 4096, max_batch: int = 64, **kw) -> List[torch.Tensor]:
+                       max_padded_tokens: int = 4096, max_batch: int = 64, sdp_noise=None, prior_noise=None,
+                       **kw) -> List[torch.Tensor]:
     """What ``Synthesizer.tts`` does one sentence at a time (TTS/utils/synthesizer.py:384-441: tokenise a sentence,
     ``model.inference`` with batch 1, append), done as a few padded batches: ``token_seqs`` are the already
     tokenised sentences, per-sentence conditioning in ``aux_input`` (``speaker_ids`` / ``d_vectors`` /
     ``language_ids``, first dimension = sentence) is carried along, and the result is one 1-D waveform (valid
     samples only) per sentence in the input order.  Utterances never interact on the path (masks are per row), so
-    a sentence's audio does not depend on what it was batched with (given the same random draws)."""
+    a sentence's audio does not depend on what it was batched with (given the same random draws) -- except, exactly as
+    in the reference's own batched ``Vits.inference``, within the decoder's receptive field of the sentence's end, where
+    a padded row sees the decoder's response to zero frames instead of the convolutions' zero padding.
+
+    ``sdp_noise`` (sequence of [2, T_i] tensors) / ``prior_noise`` (callable ``(sentence_index, channels, frames) ->
+    [channels, frames]``) pin the two random draws PER SENTENCE (tests compare with sentence-at-a-time synthesis)."""
     n = len(token_seqs)
     lengths = [len(s) for s in token_seqs]
     if any(l == 0 for l in lengths):
@@ -214,7 +220,22 @@ def synthesize_batched(model, token_seqs: Sequence[Sequence[int]], aux_input=Non
         for k in ("speaker_ids", "d_vectors", "language_ids"):
             if aux_all.get(k, None) is not None:
                 aux[k] = aux_all[k][idx].to(dev)
-        out = model.inference(tok.to(dev), aux, **kw)
+        kwb = dict(kw)
+        if sdp_noise is not None:
+            nz = torch.zeros(len(bucket), 2, tmax)
+            for j, i in enumerate(bucket):
+                nz[j, :, : lengths[i]] = sdp_noise[i]
+            kwb["sdp_noise"] = nz
+        if prior_noise is not None:
+            def rows(shape, y_lengths, bucket=bucket):
+                out_ = torch.zeros(shape)
+                for j, i in enumerate(bucket):
+                    n = int(y_lengths[j])
+                    out_[j, :, :n] = prior_noise(i, shape[1], n)
+                return out_.to(dev)
+            rows.wants_lengths = True
+            kwb["prior_noise"] = rows
+        out = model.inference(tok.to(dev), aux, **kwb)
         valid = out["wav_lengths"].tolist()
         for j, i in enumerate(bucket):
             result[i] = out["model_outputs"][j, 0, : int(valid[j])]
@@ -233,6 +254,18 @@ def concat_sentences(wavs: Sequence[torch.Tensor], gap: int = 10000) -> torch.Te
 
 def to_int16(wav: torch.Tensor) -> torch.Tensor:
     """The peak normalisation ``save_wav`` applies before writing (TTS/utils/audio/numpy_transforms.py:438-440):
-    ``wav * (32767 / max(0.01, max|wav|))`` truncated to int16."""
+    ``wav * (32767 / max(0.01, max|wav|))`` truncated to int16.  CUDA tensors go through the device kernels
+    (``b200tts_absmax`` / ``b200tts_to_int16``, no host round trip); host tensors use the same arithmetic in torch."""
+    if wav.is_cuda:
+        from .vocoder import wav_to_int16
+        return wav_to_int16(wav)
     peak = float(wav.abs().max()) if wav.numel() else 0.0
     return (wav * (32767.0 / max(0.01, peak))).to(torch.int16)
+
+
+def synthesize_to_int16(model, token_seqs: Sequence[Sequence[int]], aux_input=None, gap: int = 10000, **kw) -> torch.Tensor:
+    """``Synthesizer.tts`` + ``save_wav`` for already tokenised sentences, entirely on the device: batched synthesis,
+    sentences joined with ``gap`` zero samples (synthesizer.py:440-441), one peak over the whole utterance and the int16
+    conversion (numpy_transforms.py:439-441).  Returns the int16 samples ``save_wav`` would write (CUDA tensor)."""
+    wavs = synthesize_batched(model, token_seqs, aux_input, **kw)
+    return to_int16(concat_sentences(wavs, gap))

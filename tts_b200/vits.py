@@ -341,7 +341,10 @@ class Vits(nn.Module):
         if prior_noise is None:
             noise = torch.randn((x.shape[0], c, t_dec), dtype=torch.float32, device=x.device)
         elif callable(prior_noise):
-            noise = prior_noise((x.shape[0], c, t_dec))
+            if getattr(prior_noise, "wants_lengths", False):     # per-row draws (parallel.synthesize_batched)
+                noise = prior_noise((x.shape[0], c, t_dec), y_lengths.tolist())
+            else:
+                noise = prior_noise((x.shape[0], c, t_dec))
         else:
             noise = prior_noise
         with _Stage(self, "expand_prior"):
