@@ -242,21 +242,26 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             i_raw[e] = (idx < 2 * ROWS) ? (4 * sl) * RAWW + r : -1;
             i_dst[e] = (int)(sl * slabA) + r * 16;
         }
-        int iss_it = -1, iss_b = 0, iss_q0 = 0, iss_Tin = 0;   // the tile the cp.async front is in (decoded once per tile)
-        int tr_it = -1, tr_q0 = 0;                                // the tile the transform is in
+        // running positions instead of divisions / modulos per chunk (this loop is on the critical path of the K <= 7 layers)
+        int iss_it = 0, iss_c = 0, iss_ring = 0, iss_b = 0, iss_q0 = 0, iss_Tin = 0;   // cp.async front: tile, chunk, raw slot
+        bool iss_new = true;
+        int tr_it = 0, tr_c = 0, tr_ring = 0, tr_q0 = 0, as = 0;                       // transform: tile, chunk, raw slot, A stage
+        uint32_t pa_empty = 1;                                    // parity to wait for on A_EMPTY[as]: round 1 -> 0, round 2 -> 1, ...
+        bool tr_new = true;
+        const bool no_cp = (a.dbg & 1) != 0;
         auto issue = [&](int g) {
-            if (g < total && !(a.dbg & 1)) {
-                const int it = g / nchunks, c = g - it * nchunks;
-                if (it != iss_it) {
+            if (g < total && !no_cp) {
+                if (iss_new) {
                     int rt_;
-                    decode(it, iss_b, rt_, iss_q0);
+                    decode(iss_it, iss_b, rt_, iss_q0);
                     iss_Tin = input_extent(iss_b);
-                    iss_it = it;
+                    iss_new = false;
                 }
+                const int c = iss_c;
                 const int b = iss_b, q0 = iss_q0, Tin_b = iss_Tin;
                 const int tal = ((q0 - a.pad) & ~3);                     // 16-byte aligned window start (may be < 0)
                 const float* xb = a.x + (long long)b * a.x_bs;
-                const uint32_t dst0 = smem_u32(smRaw + (g % NRAW) * rawStage);
+                const uint32_t dst0 = smem_u32(smRaw + iss_ring * rawStage);
 #pragma unroll
                 for (int e = 0; e < MAXV; ++e) {
                     if (v_ch[e] < 0) continue;
@@ -270,7 +275,9 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                     const float* src = xb + (long long)(cg < a.Cin ? cg : 0) * a.x_cs + tsafe;
                     cp_async16_zfill(dst0 + (uint32_t)v_off[e] * 4u, src, (uint32_t)nb);
                 }
+                if (++iss_c == nchunks) { iss_c = 0; ++iss_it; iss_new = true; }
             }
+            if (++iss_ring == NRAW) iss_ring = 0;
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         for (int g = 0; g < NRAW - 1; ++g) issue(g);
@@ -278,18 +285,16 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             asm volatile("cp.async.wait_group %0;" ::"n"(NRAW - 2) : "memory");
             named_bar_sync(1, NPROD);                                     // everyone's copies of chunk g have landed
             issue(g + NRAW - 1);                                          // refills the stage transformed last iteration
-            const int as = g % NA2;
-            if (g >= NA2) ok = mbar_wait(BAR(A_EMPTY + as), ((g / NA2) - 1) & 1, a.err);
+            if (g >= NA2) ok = mbar_wait(BAR(A_EMPTY + as), pa_empty, a.err);
             if (!ok) break;
-            const int it = g / nchunks;
-            if (it != tr_it) {
+            if (tr_new) {
                 int b_, rt_;
-                decode(it, b_, rt_, tr_q0);
-                tr_it = it;
+                decode(tr_it, b_, rt_, tr_q0);
+                tr_new = false;
             }
             const int q0 = tr_q0;
             const int tin0 = q0 - a.pad, off = tin0 - (tin0 & ~3);
-            const float* raw = reinterpret_cast<const float*>(smRaw + (g % NRAW) * rawStage) + off;
+            const float* raw = reinterpret_cast<const float*>(smRaw + tr_ring * rawStage) + off;
             unsigned char* base = smA + as * stageA;
             float u[MAXI][4];
             if (!(a.dbg & 2)) {
@@ -319,6 +324,9 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A_FULL + as));       // one arrival per producer warp
+            if (++tr_c == nchunks) { tr_c = 0; ++tr_it; tr_new = true; }
+            if (++tr_ring == NRAW) tr_ring = 0;
+            if (++as == NA2) { as = 0; pa_empty ^= 1u; }
             if (ptid == 0) { if (g == 0) TC3_STAMP(1); if (g == nchunks - 1) TC3_STAMP(2); if (g == 2 * nchunks - 1) TC3_STAMP(3); if (g == 4 * nchunks - 1) TC3_STAMP(4); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -439,8 +447,8 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             const bool relu = a.relu != 0, do_store = !(a.dbg & 8);
             const float scale = a.scale, post_div = a.post_div;
             bool fast = false;                                            // interior tile: no bounds checks at all
-            auto prefetch = [&](const float* rr, int q, float* dst) {     // residual values of one column group -> registers
-                if (!has_res) return;
+            auto prefetch_any = [&](const float* rr, int q, float* dst) {   // values of one column group of a row -> registers
+
 #pragma unroll
                 for (int j = 0; j < NV / 4; ++j) {
                     const int qq = q + 4 * j;
@@ -452,6 +460,8 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                     }
                 }
             };
+            auto prefetch = [&](const float* rr, int q, float* dst) { if (has_res) prefetch_any(rr, q, dst); };
+            auto prefetch_acc = [&](const float* rr, int q, float* dst) { if (rr) prefetch_any(rr, q, dst); };
             for (int it = 0; it < my_tiles && ok; ++it) {
                 const int buf = it & 1;
                 int b, rt, q0;
@@ -459,10 +469,16 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 const float* rrow = has_res ? a.res + (long long)b * a.res_bs + (long long)co * a.res_cs : nullptr;
                 const int cend = half ? a.tstep : min(128, a.tstep);
                 fast = vec_ok && (q0 + a.tstep <= a.Tout);
-                float rv[NV], rn[NV];
-                // the first two column groups' residuals are requested before waiting for the accumulator
-                prefetch(rrow, q0 + cbeg + coff, rv);
-                if (cbeg + 16 < cend) prefetch(rrow, q0 + cbeg + 16 + coff, rn);
+                // Residual / accumulate values are prefetched TWO column groups ahead into three rotating register sets that
+                // are never copied: a register move of a pending load's result waits for the load, which made every group
+                // pay a full memory latency (r02 timeline: ~1.5 k cycles per 16-column group, the narrow stages' bound).
+                float rA[NV], rB[NV], rC[NV], oA[NV], oB[NV], oC[NV];
+                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs;
+                const float* orow = acc_r ? yrow : nullptr;
+                // the first two column groups are requested before waiting for the accumulator
+                prefetch(rrow, q0 + cbeg + coff, rA);
+                prefetch_acc(orow, q0 + cbeg + coff, oA);
+                if (cbeg + 16 < cend) { prefetch(rrow, q0 + cbeg + 16 + coff, rB); prefetch_acc(orow, q0 + cbeg + 16 + coff, oB); }
                 ok = mbar_wait(BAR(ACC_FULL + buf), (it >> 1) & 1, a.err);
                 if (!ok) break;
                 tc_fence_after();
@@ -470,18 +486,11 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 const uint32_t dlane = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16);
                 float bias = a.bias[co];
                 if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + co);
-                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs;
-#pragma unroll 1
-                for (int cg = cbeg; cg < cend; cg += 16) {
-                    float rf[NV];
-                    if (cg + 32 < cend) prefetch(rrow, q0 + cg + 32 + coff, rf);
+                auto group = [&](int cg, const float* rv, const float* ov, float* rf, float* of) {
+                    if (cg + 32 < cend) { prefetch(rrow, q0 + cg + 32 + coff, rf); prefetch_acc(orow, q0 + cg + 32 + coff, of); }
                     {
-                    float S[8], ov[NV];
+                    float S[8];
                     const int q = q0 + cg + coff;
-                    if (acc_r) {          // accumulate-into-destination (two layers per stage): loaded in place
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) ov[i] = yrow[min(q + i, a.Tout - 1)];
-                    }
                     if constexpr (DIL > 0) {
                         // TMEM reads run at ~64 B/clk per SM: one window [cg, cg + 16 + (GRP-1)*DIL) serves all
                         // groups.  Lane (c, g) needs P[i] = w[i + g*DIL]; the first reduce-scatter step sends
@@ -563,8 +572,12 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         }
                     }
                     }
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) { rv[i] = rn[i]; rn[i] = rf[i]; }
+                };
+#pragma unroll 1
+                for (int cg = cbeg; cg < cend; cg += 48) {
+                    group(cg, rA, oA, rC, oC);
+                    if (cg + 16 < cend) group(cg + 16, rB, oB, rA, oA);
+                    if (cg + 32 < cend) group(cg + 32, rC, oC, rB, oB);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -703,9 +716,10 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 const bool vec_ok = ((ycs_eff & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
                                     ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
                                     (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-                float rv[16], ov[16];
                 // order-enforced software pipeline: the (volatile) loads of group j+1 are issued before the (volatile)
-                // TMEM load of group j.  float4 per lane along time (each lane owns one output row).
+                // TMEM load of group j, into the OTHER of two register sets -- never copied (a move of a pending load's
+                // result waits for the load and would serialise the groups).  float4 per lane along time (lane = one row).
+                float rA[16], oA[16], rB[16], oB[16];
                 auto prefetch = [&](int cg, float* r_, float* o_) {
                     const int q = qb + cg;
 #pragma unroll
@@ -725,9 +739,8 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                     }
                 };
                 const bool ld_ok = rok && !(a.dbg & 4), st_ok = rok && !(a.dbg & 8);
-                if (ld_ok) prefetch(0, rv, ov);
-                for (int cg = 0; cg < 128; cg += 16) {
-                    float v[16], rn[16], on[16];
+                auto group = [&](int cg, const float* rv, const float* ov, float* rn, float* on) {
+                    float v[16];
                     if (ld_ok && cg + 16 < 128) prefetch(cg + 16, rn, on);
                     tmem_ld16(dbase + (uint32_t)cg, v);
                     const int q = qb + cg;
@@ -756,8 +769,12 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                             }
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { rv[i] = rn[i]; ov[i] = on[i]; }
+                };
+                if (ld_ok) prefetch(0, rA, oA);
+#pragma unroll 1
+                for (int cg = 0; cg < 128; cg += 32) {
+                    group(cg, rA, oA, rB, oB);
+                    group(cg + 16, rB, oB, rA, oA);
                 }
             } else {
                 // polyphase store: row r = co*ups + ph, column q -> y[co][q*ups + ph]; a warp's 32 lanes cover whole
