@@ -817,11 +817,11 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         t.B = io.B; t.n_ttiles = (a.Tq + tc3::TT2 - 1) / tc3::TT2; t.n_rtiles = n_rtiles;
         t.err = g_tc_err;
         static int staged = -1;
-        if (staged < 0) { const char* e = getenv("B200TTS_NO_STAGED"); staged = (e && atoi(e)) ? 0 : 1; }
+        if (staged < 0) { const char* e = getenv("B200TTS_STAGED"); staged = (e && atoi(e)) ? 1 : 0; }
         size_t smem3 = tc3::smem_bytes3(rows_pad, rows_pad + 4);
-        // staged (shared-memory transposed, coalesced) epilogue: 13 % faster on the epilogue-bound K <= 3 layers and 5-7 %
-        // slower on the MMA-bound K = 7 / 11 ones (its shared-memory traffic competes with the operand fetch), so only
-        // short-kernel layers take it.  On by default since r02 (whole GPU suite green); B200TTS_NO_STAGED=1 disables it
+        // staged (shared-memory transposed, coalesced) epilogue for K <= 3 layers.  It beat the r01 direct epilogue by 13 % on
+        // those layers; since the direct epilogue prefetches without register copies (r02) the direct one wins
+        // (decoder 17.2 -> 16.5 ms per bench step, same box A/B), so it is opt-in again: B200TTS_STAGED=1
         if (staged && L.K <= 3 && L.ups == 1 && !t.gate && t.split == 0 && ((smem3 + 15) / 16 * 16 + tc3::STAGE_BYTES) <= 227 * 1024) {
             t.stage = 1;
             t.stage_off = (int)((smem3 + 15) / 16 * 16);
