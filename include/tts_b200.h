@@ -76,6 +76,16 @@ size_t b200tts_mas_workspace_bytes(int B, int Tx, int Ty);
 int b200tts_mas(const float* value, const float* mask, const int32_t* t_x, const int32_t* t_y, int B, int Tx,
                 int Ty, void* path, int path_is_f32, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Alignment straight from the prior statistics: replaces the body of Vits.forward_mas up to `attn`
+ * (TTS/tts/models/vits.py:909-919): logp[b,x,y] = sum_c exp(-2 logs_p)(-0.5 z_p^2) + sum_c (m_p exp(-2 logs_p)) z_p
+ * + sum_c(-0.5 log 2pi - logs_p) + sum_c(-0.5 m_p^2 exp(-2 logs_p)), then maximum_path(logp, mask) with
+ * t_x / t_y = the lengths the masks encode.  z_p [B,C,Ty], m_p / logs_p [B,C,Tx]; path as b200tts_mas; logp_out
+ * (nullable) [B,Tx,Ty] receives the log-likelihoods (otherwise they live in the workspace only). */
+size_t b200tts_mas_from_stats_workspace_bytes(int B, int Tx, int Ty);
+int b200tts_mas_from_stats(const float* z_p, const float* m_p, const float* logs_p, const int32_t* t_x, const int32_t* t_y,
+                           int B, int C, int Tx, int Ty, void* path, int path_is_f32, float* logp_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- HiFiGAN generator -----------------------------------------------------------------------
  * Replaces HifiganGenerator.forward, TTS/vocoder/models/hifigan_generator.py:236-265
  * (ctor arguments :163-178).

@@ -679,3 +679,17 @@ def wav_to_int16(wav):
     wav = np.asarray(wav, dtype=np.float32)
     wav_norm = wav * (32767 / max(0.01, np.max(np.abs(wav))))
     return wav_norm.astype(np.int16)
+
+
+# --------------------------------------------------------------------------- training-side alignment
+def forward_mas_attn(z_p, m_p, logs_p, x_mask, y_mask, impl="c"):
+    """The alignment half of Vits.forward_mas, tts/models/vits.py:909-919: attn [B,1,Tx,Ty] (and logp)."""
+    attn_mask = torch.unsqueeze(x_mask, -1) * torch.unsqueeze(y_mask, 2)
+    o_scale = torch.exp(-2 * logs_p)
+    logp1 = torch.sum(-0.5 * math.log(2 * math.pi) - logs_p, [1]).unsqueeze(-1)
+    logp2 = torch.einsum("klm, kln -> kmn", [o_scale, -0.5 * (z_p ** 2)])
+    logp3 = torch.einsum("klm, kln -> kmn", [m_p * o_scale, z_p])
+    logp4 = torch.sum(-0.5 * (m_p ** 2) * o_scale, [1]).unsqueeze(-1)
+    logp = logp2 + logp3 + logp1 + logp4
+    attn = maximum_path(logp, attn_mask.squeeze(1), impl=impl).unsqueeze(1)
+    return attn, logp

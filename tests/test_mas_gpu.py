@@ -89,3 +89,23 @@ def test_full_size_cfg4_bit_exact_and_structure():
         d = idx[n, 1:ny] - idx[n, :ny - 1]
         assert d.min() >= 0 and d.max() <= 1
         assert idx[n, 0] == 0 and idx[n, ny - 1] == nx - 1
+
+
+@pytest.mark.parametrize("b,c,tx,ty", [(3, 192, 37, 151), (8, 192, 64, 300), (2, 24, 5, 9)])
+def test_alignment_from_prior_statistics_matches_oracle(b, c, tx, ty):
+    """the alignment step of Vits.forward_mas (vits.py:909-919) from z_p / m_p / logs_p on the device."""
+    from tts_b200.helpers import maximum_path_from_stats
+    torch.manual_seed(b * 100 + tx)
+    xl = torch.randint(max(1, tx // 2), tx + 1, (b,))
+    xl[0] = tx
+    yl = torch.clamp(xl * torch.randint(2, 5, (b,)), max=ty)
+    yl[0] = ty
+    x_mask = O.sequence_mask(xl, tx).unsqueeze(1).float()
+    y_mask = O.sequence_mask(yl, ty).unsqueeze(1).float()
+    z_p, m_p, logs_p = torch.randn(b, c, ty), torch.randn(b, c, tx), torch.randn(b, c, tx) * 0.3
+    want, want_logp = O.forward_mas_attn(z_p, m_p, logs_p, x_mask, y_mask)
+    got, logp = maximum_path_from_stats(z_p.cuda(), m_p.cuda(), logs_p.cuda(), x_mask.cuda(), y_mask.cuda(), return_logp=True)
+    rel = (logp.cpu() - want_logp).abs().max() / want_logp.abs().max()
+    assert rel < 2e-6, rel                              # same arithmetic, different summation order over channels
+    assert torch.equal(got.cpu(), want), "alignment path differs"
+    assert torch.equal(got.sum(2).cpu(), want.sum(2))    # one text position per frame

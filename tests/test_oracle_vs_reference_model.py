@@ -136,3 +136,26 @@ def test_voice_conversion_glue_bit_exact(R):
     go, gm, (gz, gzp, gzh) = O.voice_conversion(sd, y, lens, g(src), g(tgt), noise, args=dataclasses.asdict(args))
     for a, b in ((go, o_hat), (gm, y_mask), (gz, z), (gzp, z_p), (gzh, z_hat)):
         assert torch.equal(a, b)
+
+
+@torch.no_grad()
+def test_forward_mas_alignment_vs_real_model(R):
+    """Vits.forward_mas (vits.py:909-919) on the real model class: the oracle's logp / attn restatement is bit-exact
+    (the real maximum_path runs the reference's compiled Cython kernel)."""
+    args = _small_args(R)
+    cfg = R["vits_config"].VitsConfig()
+    cfg.model_args = args
+    cfg.__post_init__()
+    torch.manual_seed(12)
+    m = R["vits_model"].Vits(cfg).train()
+    b, c, tx, ty = 3, 192, 11, 47
+    xl, yl = torch.tensor([11, 7, 4]), torch.tensor([47, 30, 21])
+    x_mask = O.sequence_mask(xl, tx).unsqueeze(1).float()
+    y_mask = O.sequence_mask(yl, ty).unsqueeze(1).float()
+    z_p, m_p, logs_p = torch.randn(b, c, ty), torch.randn(b, c, tx), torch.randn(b, c, tx) * 0.3
+    x = torch.randn(b, c, tx)
+    outputs, attn = m.forward_mas({}, z_p, m_p, logs_p, x, x_mask, y_mask, g=None, lang_emb=None)
+    got, _ = O.forward_mas_attn(z_p, m_p, logs_p, x_mask, y_mask, impl="ref")
+    assert torch.equal(got, attn)
+    got_c, _ = O.forward_mas_attn(z_p, m_p, logs_p, x_mask, y_mask, impl="c")
+    assert torch.equal(got_c, attn)

@@ -107,6 +107,10 @@ def _declare(lib):
     lib.b200tts_mas_workspace_bytes.argtypes = [ci, ci, ci]
     lib.b200tts_mas.restype = ci
     lib.b200tts_mas.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, sz, vp]
+    lib.b200tts_mas_from_stats_workspace_bytes.restype = sz
+    lib.b200tts_mas_from_stats_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.b200tts_mas_from_stats.restype = ci
+    lib.b200tts_mas_from_stats.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, ci, vp, vp, sz, vp]
     lib.b200tts_hifigan_create.restype = ci
     lib.b200tts_hifigan_create.argtypes = [ctypes.POINTER(HifiganConfigC), ctypes.POINTER(vp), ci,
                                            ctypes.POINTER(vp)]

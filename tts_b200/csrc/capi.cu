@@ -68,6 +68,14 @@ int b200tts_mas(const float* value, const float* mask, const int32_t* t_x, const
                        (cudaStream_t)stream);
 }
 
+size_t b200tts_mas_from_stats_workspace_bytes(int B, int Tx, int Ty) { return mas_from_stats_workspace_bytes(B, Tx, Ty); }
+int b200tts_mas_from_stats(const float* z_p, const float* m_p, const float* logs_p, const int32_t* t_x, const int32_t* t_y,
+                           int B, int C, int Tx, int Ty, void* path, int path_is_f32, float* logp_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    return mas_from_stats(z_p, m_p, logs_p, t_x, t_y, B, C, Tx, Ty, path, path_is_f32, logp_out, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
 int b200tts_hifigan_create(const b200tts_hifigan_config* cfg, const float* const* weights, int num_weights,
                            b200tts_hifigan** out) {
     if (!cfg || !weights || !out) { set_error("hifigan_create: null argument"); return 1; }

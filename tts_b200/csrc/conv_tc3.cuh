@@ -333,23 +333,38 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         if (ptid == 0) TC3_STAMP(5);
     } else if (warp == 8) {
         // ============================================================ weight loader
-        if (lane == 0) {
-            bool ok = true;
-            int gi = 0;
+        // One lane per ring slot: lane s owns slot s and feeds it with tap blocks s, s + NB2, s + 2*NB2, ... of this CTA's
+        // block sequence.  A single thread walking the ring paid its wait -> expect_tx -> bulk-copy chain (~400 cycles) once
+        // per 8 KB block -- measured as a 20 B/clk "L2 limit" that was really this thread (r02 ablation: the kernel without
+        // MMAs still took 75 % of its time).  Ten independent chains keep ten copies in flight.
+        if (lane < NB2) {
             const int total = nchunks * K;                                 // tap blocks per tile (contiguous in memory)
-            for (int it = 0; it < my_tiles && ok; ++it) {
-                int b, rt, q0;
-                decode(it, b, rt, q0);
-                const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(a.w) + (size_t)rt * total * stageB;
-                for (int j = 0; j < total && ok; ++j, ++gi) {
-                    const int st = gi % NB2;
-                    if (gi >= NB2) ok = mbar_wait(BAR(B_EMPTY + st), ((gi / NB2) - 1) & 1, a.err);
-                    if (!ok) break;
-                    mbar_expect_tx(BAR(B_FULL + st), stageB);
-                    bulk_g2s(smem_u32(smB + st * stageB), wsrc + (size_t)j * stageB, stageB, BAR(B_FULL + st));
+            const long long all = (long long)my_tiles * total;
+            const uint32_t full = BAR(B_FULL + lane), empty = BAR(B_EMPTY + lane);
+            const uint32_t dst = smem_u32(smB + lane * stageB);
+            int it = 0, j = lane;                                          // block gi = it * total + j
+            while (j >= total && it < my_tiles) { j -= total; ++it; }
+            int cur_it = -1;
+            const unsigned char* wsrc = nullptr;
+            uint32_t par = 1;                                              // parity of B_EMPTY to wait for: round 1 -> 0, 2 -> 1
+            bool ok = true, first = true;
+            for (long long gi = lane; gi < all && ok; gi += NB2) {
+                if (it != cur_it) {
+                    int b_, rt, q0_;
+                    decode(it, b_, rt, q0_);
+                    wsrc = reinterpret_cast<const unsigned char*>(a.w) + (size_t)rt * total * stageB;
+                    cur_it = it;
                 }
+                if (!first) { ok = mbar_wait(empty, par, a.err); if (!ok) break; }
+                mbar_expect_tx(full, stageB);
+                bulk_g2s(dst, wsrc + (size_t)j * stageB, stageB, full);
+                first = false;
+                par ^= 1u;
+                j += NB2;
+                while (j >= total) { j -= total; ++it; }
             }
         }
+        __syncwarp();
     } else if (warp == 9) {
         // ============================================================ MMA issuer
         // ncu (profiles/r02_tc3_issue_loop.md): this ONE thread is what bounds the MMA-heavy layers -- it never waits long

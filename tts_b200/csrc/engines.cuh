@@ -158,5 +158,8 @@ int launch_to_int16(const float* x, long long n, const unsigned* peak_bits, shor
 size_t mas_workspace_bytes(int B, int Tx, int Ty);
 int mas_forward(const float* value, const float* mask, const int* t_x, const int* t_y, int B, int Tx, int Ty,
                 void* path, int path_is_f32, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t mas_from_stats_workspace_bytes(int B, int Tx, int Ty);
+int mas_from_stats(const float* z_p, const float* m_p, const float* logs_p, const int* t_x, const int* t_y, int B, int C,
+                   int Tx, int Ty, void* path, int path_is_f32, float* logp_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace b200tts

@@ -620,3 +620,103 @@ int mas_forward(const float* value, const float* mask, const int* t_x, const int
 }
 
 }  // namespace b200tts
+
+// ------------------------------------------------------------------ alignment from the prior statistics (training side)
+// Vits.forward_mas, TTS/tts/models/vits.py:909-919: the log-likelihood of every (text position, frame) pair
+//   logp = [sum_c o*(-0.5 z^2)] + [sum_c (m*o)*z] + sum_c(-0.5 log 2pi - logs) + sum_c(-0.5 m^2 o),   o = exp(-2 logs)
+// (two einsums + two row sums, added in that order), then maximum_path(logp, mask).  Here one kernel forms logp
+// ([64 x 64] tiles per CTA, 16-channel stages through shared memory, exp / squares computed on the way in, FP32 FMA in
+// ascending channel order) and the MAS kernel above consumes it; the reference materialises five [B,Tx,Ty] / [B,C,*]
+// temporaries and round-trips logp through the host.
+namespace b200tts {
+namespace {
+
+constexpr int LP_T = 64, LP_KC = 16;
+
+__global__ void __launch_bounds__(256) mas_logp_kernel(const float* __restrict__ z_p, const float* __restrict__ m_p,
+                                                      const float* __restrict__ logs_p, float* __restrict__ logp, int C,
+                                                      int Tx, int Ty) {
+    __shared__ float sO[LP_KC][LP_T + 1], sMO[LP_KC][LP_T + 1], sL[LP_KC][LP_T + 1], sM2O[LP_KC][LP_T + 1];
+    __shared__ float sZ[LP_KC][LP_T + 1], sZ2[LP_KC][LP_T + 1];
+    const int b = blockIdx.z, x0 = blockIdx.y * LP_T, y0 = blockIdx.x * LP_T;
+    const int tid = threadIdx.x, tx = tid >> 4, ty = tid & 15;          // thread -> 4 x-rows (tx*4..) x 4 y-columns (ty + 16 j)
+    const float* zb = z_p + (size_t)b * C * Ty;
+    const float* mb = m_p + (size_t)b * C * Tx;
+    const float* lb = logs_p + (size_t)b * C * Tx;
+    float acc2[4][4], acc3[4][4], l1[4], l4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        l1[i] = 0.f; l4[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc2[i][j] = 0.f; acc3[i][j] = 0.f; }
+    }
+    const float half_log_2pi = 0.91893853320467274178f;                   // 0.5 * log(2 pi)
+    for (int c0 = 0; c0 < C; c0 += LP_KC) {
+        for (int i = tid; i < LP_KC * LP_T; i += 256) {
+            const int c = i / LP_T, t = i - c * LP_T, cg = c0 + c;
+            float o = 0.f, mo = 0.f, ls = 0.f, m2o = 0.f, z = 0.f, z2 = 0.f;
+            if (cg < C) {
+                if (x0 + t < Tx) {
+                    const float lg = lb[(size_t)cg * Tx + x0 + t], m = mb[(size_t)cg * Tx + x0 + t];
+                    o = expf(-2.f * lg);
+                    mo = __fmul_rn(m, o);
+                    ls = -half_log_2pi - lg;
+                    m2o = __fmul_rn(__fmul_rn(-0.5f, __fmul_rn(m, m)), o);
+                }
+                if (y0 + t < Ty) {
+                    z = zb[(size_t)cg * Ty + y0 + t];
+                    z2 = __fmul_rn(-0.5f, __fmul_rn(z, z));
+                }
+            }
+            sO[c][t] = o; sMO[c][t] = mo; sL[c][t] = ls; sM2O[c][t] = m2o; sZ[c][t] = z; sZ2[c][t] = z2;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < LP_KC; ++c) {
+            float o[4], mo[4], zz[4], zz2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { o[i] = sO[c][tx * 4 + i]; mo[i] = sMO[c][tx * 4 + i]; l1[i] += sL[c][tx * 4 + i]; l4[i] += sM2O[c][tx * 4 + i]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { zz[j] = sZ[c][ty + 16 * j]; zz2[j] = sZ2[c][ty + 16 * j]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acc2[i][j] = fmaf(o[i], zz2[j], acc2[i][j]); acc3[i][j] = fmaf(mo[i], zz[j], acc3[i][j]); }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + tx * 4 + i;
+        if (x >= Tx) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int y = y0 + ty + 16 * j;
+            if (y < Ty) logp[((size_t)b * Tx + x) * Ty + y] = __fadd_rn(__fadd_rn(__fadd_rn(acc2[i][j], acc3[i][j]), l1[i]), l4[i]);
+        }
+    }
+}
+
+}  // namespace
+
+size_t mas_from_stats_workspace_bytes(int B, int Tx, int Ty) {
+    return (((size_t)B * Tx * Ty * sizeof(float) + 255) & ~size_t(255)) + mas_workspace_bytes(B, Tx, Ty);
+}
+
+int mas_from_stats(const float* z_p, const float* m_p, const float* logs_p, const int* t_x, const int* t_y, int B, int C,
+                   int Tx, int Ty, void* path, int path_is_f32, float* logp_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    B200_REQUIRE(z_p && m_p && logs_p && t_x && t_y && path, "mas_from_stats: null pointer");
+    if (B == 0 || Tx == 0 || Ty == 0) return 0;
+    B200_REQUIRE(ws && ws_bytes >= mas_from_stats_workspace_bytes(B, Tx, Ty), "mas_from_stats: workspace too small");
+    const size_t lp_bytes = ((size_t)B * Tx * Ty * sizeof(float) + 255) & ~size_t(255);
+    float* logp = logp_out ? logp_out : reinterpret_cast<float*>(ws);
+    dim3 grid((Ty + LP_T - 1) / LP_T, (Tx + LP_T - 1) / LP_T, B);
+    B200_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "mas_from_stats: grid too large");
+    mas_logp_kernel<<<grid, 256, 0, st>>>(z_p, m_p, logs_p, logp, C, Tx, Ty);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return mas_forward(logp, nullptr, t_x, t_y, B, Tx, Ty, path, path_is_f32, reinterpret_cast<char*>(ws) + lp_bytes,
+                       ws_bytes - lp_bytes, st);
+}
+
+}  // namespace b200tts

@@ -62,3 +62,27 @@ def generate_path(duration, mask):
     path = sequence_mask(cum, t_y).to(mask.dtype).view(b, t_x, t_y)
     path = path - torch.nn.functional.pad(path, (0, 0, 1, 0))[:, :-1]
     return path * mask
+
+
+def maximum_path_from_stats(z_p, m_p, logs_p, x_mask, y_mask, return_logp=False):
+    """The alignment step of ``Vits.forward_mas`` (TTS/tts/models/vits.py:909-919) on the device: builds the
+    log-likelihood ``logp`` [B,Tx,Ty] of every (text position, frame) pair from the prior statistics and runs the
+    monotonic alignment search on it.  z_p [B,C,Ty]; m_p, logs_p [B,C,Tx]; x_mask [B,1,Tx]; y_mask [B,1,Ty].
+    Returns ``attn`` [B,1,Tx,Ty] (0/1, float32) like the reference (and ``logp`` when asked)."""
+    _lib.require_cuda(z_p, "z_p")
+    z_p, m_p, logs_p = (t.to(torch.float32).contiguous() for t in (z_p, m_p, logs_p))
+    b, c, ty = z_p.shape
+    tx = m_p.shape[-1]
+    t_x = x_mask.reshape(b, -1).to(torch.float32).sum(1).to(torch.int32).contiguous()
+    t_y = y_mask.reshape(b, -1).to(torch.float32).sum(1).to(torch.int32).contiguous()
+    path = torch.empty((b, tx, ty), dtype=torch.float32, device=z_p.device)
+    logp = torch.empty((b, tx, ty), dtype=torch.float32, device=z_p.device) if return_logp else None
+    L = _lib.lib()
+    with torch.cuda.device(z_p.device):
+        ws = _lib.workspace(z_p.device, L.b200tts_mas_from_stats_workspace_bytes(b, tx, ty), "mas_from_stats")
+        rc = L.b200tts_mas_from_stats(_lib.ptr(z_p), _lib.ptr(m_p), _lib.ptr(logs_p), _lib.ptr(t_x), _lib.ptr(t_y), b, c, tx,
+                                      ty, _lib.ptr(path), 1, _lib.ptr(logp), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                      _lib.stream_ptr(z_p.device))
+    _lib.check(rc, "mas_from_stats")
+    attn = path.unsqueeze(1)
+    return (attn, logp) if return_logp else attn
