@@ -1,3 +1,5 @@
+// Second-generation tcgen05 conv kernel (persistent, M = time).  Kept for the stand-alone harness only; the library
+// (tts_b200/csrc) does not include or launch it.
 // Persistent tcgen05 3xTF32 conv1d (second generation of conv_tc.cuh; same math, same operand layouts).
 //
 // One CTA per SM loops over (batch, row-tile, time-tile) work items; every pipeline runs continuously across
@@ -15,7 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "conv_tc.cuh"   // descriptor / barrier helpers
+#include "conv_tc_v1.cuh"   // first generation + the shared descriptor / barrier helpers
 
 namespace b200tts {
 namespace tc2 {

@@ -6,7 +6,7 @@
 #include <string.h>
 #include <vector>
 
-#include "../tts_b200/csrc/conv_tc2.cuh"
+#include "legacy/conv_tc2.cuh"
 #include "../tts_b200/csrc/conv_tc3.cuh"
 
 using namespace b200tts::tc;

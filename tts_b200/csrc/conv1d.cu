@@ -17,7 +17,6 @@
 #include "common.cuh"
 #include "engines.cuh"
 #include "conv_tc.cuh"
-#include "conv_tc2.cuh"
 #include "conv_tc3.cuh"
 
 #include <stdarg.h>
@@ -435,11 +434,10 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
     if (upload(&L.w, P.data(), P.size())) return 2;
     if (upload(&L.bias, bp.data(), bp.size())) return 2;
     // tcgen05 packing (3xTF32 hi/lo split) for layers the tensor-core kernel can take
-    // rows >= 64: tiles of 128 zero-padded rows (tcgen05 M = 128, third-generation kernel); narrower layers keep
-    // exact tiles of 32 / 16 rows for the M = time orientation
+    // rows >= 32: tiles of 128 zero-padded rows (tcgen05 M = 128); exactly 32 / 64 rows additionally get the grouped
+    // packing below (no padding), which the dispatcher prefers; fewer rows run on the FP32-FMA kernel
     L.tc_n = 0;
-    if (rows >= 64) L.tc_n = 128;
-    else for (int n : {32, 16}) if (rows % n == 0) { L.tc_n = n; break; }
+    if (rows >= 32) L.tc_n = 128;
     if (L.tc_n && rows >= 16 && Cin >= 8) {
         using namespace tc;
         const int N = L.tc_n, nt = (rows + N - 1) / N, nchunk = (Cin + KC - 1) / KC;
@@ -729,22 +727,18 @@ static void set_ragged(tc3::Tc3Args& t, const ConvKArgs& a, size_t& smem) {
 }
 
 static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& a, cudaStream_t st) {
-    static int enabled = -1, v2_enabled = -1, grouped_enabled = 1;
+    static int enabled = -1, grouped_enabled = 1;
     if (enabled < 0) {
         const char* e3 = getenv("B200TTS_NO_TCG");
         grouped_enabled = (e3 && atoi(e3)) ? 0 : 1;
         const char* e = getenv("B200TTS_NO_TC");
         enabled = (e && atoi(e)) ? 0 : 1;
-        const char* e2 = getenv("B200TTS_NO_TC2");
-        v2_enabled = (e2 && atoi(e2)) ? 0 : 1;
     }
-    if (!enabled || !L.allow_tc || !L.w_tc || a.Tq < 128) return -1;
+    if (!enabled || !L.allow_tc || (!L.w_tc && !L.w_tcg) || a.Tq < 128) return -1;
     if (a.act == ACT_LOGCLAMP || a.act == ACT_TANH) return -1;
     const bool needs_v3 = (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2 | EPI_GATE)) != 0;
     int dev = 0;
     if (int rc = device_once(g_tc_once, &dev, [](int d) -> int {
-        B200_CUDA_OK(cudaFuncSetAttribute(tc::conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(tc2::conv1d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         for (int g : {2, 4})
@@ -765,7 +759,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
     // ---- persistent kernel (needs 16-byte aligned activation rows for its cp.async staging; no input mask)
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) && (a.x_cs % 4 == 0) && (a.x_bs % 4 == 0);
     const int n_rtiles = (L.Rows + L.tc_n - 1) / L.tc_n;
-    const bool persistent_ok = v2_enabled && aligned && !a.xmask &&
+    const bool persistent_ok = aligned && !a.xmask &&
                                (L.ups == 1 || (!a.res && !(a.flags & EPI_ACCUM) && !a.ymask && !a.cond));
     if (grouped_enabled && persistent_ok && L.tc_grp && L.w_tcg && L.ups == 1 && !needs_v3 && !a.ymask &&
         (L.tc_grp - 1) * L.dil <= 15 && a.Tq >= 256) {
@@ -796,7 +790,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             return 0;
         }
     }
-    if (persistent_ok && L.tc_n == 128 && tc3::smem_bytes3(rows_pad, rows_pad + 4) <= 227 * 1024) {
+    if (persistent_ok && L.tc_n == 128 && L.w_tc && tc3::smem_bytes3(rows_pad, rows_pad + 4) <= 227 * 1024) {
         // third generation: M = rows (128, zero padded), N = 256 time steps
         tc3::Tc3Args t;
         memset(&t, 0, sizeof(t));
@@ -836,54 +830,10 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         B200_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    if (needs_v3) return -1;   // only the third-generation kernel implements gate / split / pre-mask epilogues
-    const size_t smem2 = tc2::smem_bytes2(L.tc_n, rows_pad, rows_pad + 4);
-    if (persistent_ok && L.tc_n < 128 && smem2 <= 227 * 1024) {
-        tc2::Tc2Args t;
-        memset(&t, 0, sizeof(t));
-        t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin; t.in_slope = a.in_slope;
-        t.w = L.w_tc; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
-        t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = L.tc_n;
-        t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout; t.ups = L.ups; t.Tq = a.Tq;
-        t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
-        t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;
-        t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
-        t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
-        t.rows_pad = rows_pad; t.raw_w = rows_pad + 4;
-        t.B = io.B; t.n_ttiles = (a.Tq + tc2::TT2 - 1) / tc2::TT2; t.n_rtiles = n_rtiles;
-        t.err = g_tc_err; t.tg = tc2::taps_per_slot(L.tc_n);
-        const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
-        const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-        tc2::conv1d_tc2_kernel<<<grid, tc2::NTHREADS2, smem2, st>>>(t);
-        count_launch();
-        dispatch_note(DISPATCH_TC2);
-        B200_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
-    // ---- first-generation kernel (one tile per CTA; any alignment, optional input mask)
-    if (L.ups != 1) return -1;
-    if (tc::NSLAB * rows_pad > tc::MAXIT * tc::PGROUP) return -1;
-    const size_t smem = tc::smem_bytes(L.tc_n, rows_pad);
-    if (smem > 227 * 1024) return -1;
-    tc::TcArgs t;
-    memset(&t, 0, sizeof(t));
-    t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin;
-    t.xmask = a.xmask; t.xmask_bs = a.xmask_bs; t.in_slope = a.in_slope;
-    t.w = L.w_tc; t.bias = L.bias; t.cond = a.cond; t.cond_bs = a.cond_bs;
-    t.Cin = L.Cin; t.K = L.K; t.dil = L.dil; t.pad = L.pad; t.Rows = L.Rows; t.N = L.tc_n;
-    t.y = a.y; t.y_bs = a.y_bs; t.y_cs = a.y_cs; t.Tout = a.Tout;
-    t.res = a.res; t.res_bs = a.res_bs; t.res_cs = a.res_cs;
-    t.ymask = a.ymask; t.ymask_bs = a.ymask_bs;
-    t.scale = a.scale; t.post_div = a.post_div; t.relu = (a.act == ACT_RELU); t.accum = (a.flags & EPI_ACCUM) ? 1 : 0;
-    t.mask_post = (a.flags & EPI_MASK_POST) ? 1 : 0;
-    t.rows_pad = rows_pad; t.err = g_tc_err;
-    dim3 grid((a.Tq + tc::TT - 1) / tc::TT, n_rtiles, io.B);
-    if (grid.y > 65535 || grid.z > 65535) return -1;
-    tc::conv1d_tc_kernel<<<grid, tc::NTHREADS, smem, st>>>(t);
-    count_launch();
-    dispatch_note(DISPATCH_TC1);
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    // Everything else (fewer than 64 rows without a grouped packing, unaligned or masked inputs, shared-memory budget)
+    // runs on the exact FP32-FMA kernel: the first two tcgen05 generations are no longer part of the library
+    // (tools/legacy/, harness only), so a dispatch change cannot silently land on them.
+    return -1;
 }
 
 int conv_tc_error_flag() {   // 1 if any tcgen05 launch (on any device) hit a pipeline timeout; call after a sync
