@@ -57,7 +57,7 @@ static std::vector<float> pack_tc(const std::vector<float>& W, int Cout, int Cin
 }
 
 static std::vector<float> pack_grouped(const std::vector<float>& W, int Cout, int Cin, int K, int G) {
-    const int J = (K + G - 1) / G, nchunk = (Cin + KC - 1) / KC, cpw = 32 / G;
+    const int J = (K + G - 1) / G, nchunk = (Cin + KC - 1) / KC;
     const size_t blk = (size_t)2 * NSLAB * 128 * 4;
     std::vector<float> P((size_t)nchunk * J * blk, 0.f);
     for (int c = 0; c < nchunk; ++c)
@@ -66,7 +66,7 @@ static std::vector<float> pack_grouped(const std::vector<float>& W, int Cout, in
             for (int s = 0; s < NSLAB; ++s)
                 for (int m = 0; m < 128; ++m)
                     for (int i = 0; i < 4; ++i) {
-                        const int q = m / 32, l = m % 32, co = q * cpw + l / G, g = l % G, k = G * j + g, ci = c * KC + 4 * s + i;
+                        const int g = m / Cout, co = m % Cout, k = G * j + g, ci = c * KC + 4 * s + i;   // row = group * Cout + channel
                         float v = (ci < Cin && k < K) ? W[((size_t)co * Cin + ci) * K + k] : 0.f;
                         uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u;
                         float hi; memcpy(&hi, &u, 4);
@@ -137,14 +137,16 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
             a3.n_ttiles = (T + a3.tstep - 1) / a3.tstep; a3.n_rtiles = 1;
         }
         smem2 = smem_bytes3(a3.rows_pad, a3.raw_w);
+        if (G > 1) { smem2 = (smem2 + 127) / 128 * 128; a3.stage_off = (int)smem2; smem2 += GROUP_XCHG_BYTES; }
+        else if (!getenv("TC_STAGE")) { smem2 = (smem2 + 127) / 128 * 128; a3.stage_off = (int)smem2; smem2 += LEAN_STAGE_BYTES; }
         const bool staged = getenv("TC_STAGE") && G == 1;
         if (staged) { a3.stage = 1; a3.stage_off = (int)((smem2 + 15) / 16 * 16); smem2 = (size_t)a3.stage_off + STAGE_BYTES; CK(cudaFuncSetAttribute(conv1d_tc3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); }
-        if (G > 1) CK(cudaFuncSetAttribute(grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (G > 1) CK(cudaFuncSetAttribute(grouped_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         const int tiles = a3.B * a3.n_ttiles * a3.n_rtiles;
         grid2 = dim3(tiles < sms ? tiles : sms);
-        if (G > 1) grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        if (G > 1) grouped_kernel(G)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         else if (staged) conv1d_tc3s_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         else conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
     } else if (v2) {
@@ -184,7 +186,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (getenv("TC_TRACE") && v3) {
         unsigned long long* dtr; CK(cudaMalloc(&dtr, (size_t)grid2.x * 32 * 8)); CK(cudaMemset(dtr, 0, (size_t)grid2.x * 32 * 8));
         a3.trace = dtr;
-        if (G > 1) b200tts::tc3::grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
+        if (G > 1) b200tts::tc3::grouped_kernel(G)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         else b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3);
         CK(cudaDeviceSynchronize());
         std::vector<unsigned long long> tr((size_t)grid2.x * 32);
@@ -232,7 +234,7 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
     if (iters > 0 && herr == 0 && !accum) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
-        for (int i = 0; i < iters; ++i) { if (v3 && G > 1) b200tts::tc3::grouped_kernel(G, getenv("TC_GENERIC") ? 0 : dil)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3 && a3.stage) b200tts::tc3::conv1d_tc3s_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
+        for (int i = 0; i < iters; ++i) { if (v3 && G > 1) b200tts::tc3::grouped_kernel(G)<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3 && a3.stage) b200tts::tc3::conv1d_tc3s_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v3) b200tts::tc3::conv1d_tc3_kernel<<<grid2, b200tts::tc3::NTHREADS2, smem2>>>(a3); else if (v2) b200tts::tc2::conv1d_tc2_kernel<<<grid2, b200tts::tc2::NTHREADS2, smem2>>>(a2); else conv1d_tc_kernel<<<grid, NTHREADS, smem>>>(a); }
         cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
         printf("  %.3f ms  %.1f TFLOP/s (algorithmic fp32)", ms, 2.0 * B * Cout * (double)C * K * T / ms / 1e9);
@@ -245,7 +247,8 @@ static int run_case(int B, int C, int T, int K, int dil, int with_res, int accum
 int main(int argc, char** argv) {
     int fails = 0;
     if (argc >= 8 && !strcmp(argv[1], "one"))
-        return run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), 1, 0, atoi(argv[7]));
+        return run_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argc >= 9 ? atoi(argv[8]) : 1,
+                        argc >= 10 ? atoi(argv[9]) : 0, atoi(argv[7]));   // one B C T K dil iters [res] [accum]
     fails += run_case(1, 32, 256, 1, 1, 0, 0, 0);      // smallest: one chunk group, one tap
     fails += run_case(1, 32, 300, 3, 1, 0, 0, 0);
     fails += run_case(2, 128, 700, 11, 5, 1, 0, 0);

@@ -465,12 +465,12 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
     } else {
         L.tc_n = 0;
     }
-    // grouped packing for exactly 32 / 64 rows (conv_tc3.cuh, grouped mode): MMA row m = quarter*32 + cc*G + g holds
-    // channel co = quarter*(32/G) + cc and tap group g; tap block j carries tap G*j + g (zero beyond K)
+    // grouped packing for exactly 32 / 64 rows (conv_tc3.cuh, grouped mode): MMA row m = g * rows + co holds channel co
+    // and tap group g (a TMEM lane quarter = one group); tap block j carries tap G*j + g (zero beyond K)
     L.tc_grp = 0;
     if (L.ups == 1 && (rows == 32 || rows == 64) && Cin >= 8) {
         using namespace tc;
-        const int G = 128 / rows, J = (K + G - 1) / G, nchunk = (Cin + KC - 1) / KC, cpw = 32 / G;
+        const int G = 128 / rows, J = (K + G - 1) / G, nchunk = (Cin + KC - 1) / KC;
         const size_t blk = (size_t)2 * NSLAB * 128 * 4;
         std::vector<float> Q((size_t)nchunk * J * blk, 0.f);
         for (int c = 0; c < nchunk; ++c)
@@ -479,7 +479,7 @@ static int pack_rows(ConvLayer& L, const std::vector<float>& Wl, const std::vect
                 for (int s2 = 0; s2 < NSLAB; ++s2)
                     for (int m = 0; m < 128; ++m)
                         for (int i = 0; i < 4; ++i) {
-                            const int q = m / 32, l = m % 32, co = q * cpw + l / G, g = l % G;
+                            const int g = m / rows, co = m % rows;
                             const int k = G * j + g, ci = c * KC + 4 * s2 + i;
                             const float v = (ci < Cin && k < K) ? Wl[((size_t)co * Cin + ci) * K + k] : 0.f;
                             uint32_t u;
@@ -736,14 +736,15 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
     }
     if (!enabled || !L.allow_tc || (!L.w_tc && !L.w_tcg) || a.Tq < 128) return -1;
     if (a.act == ACT_LOGCLAMP || a.act == ACT_TANH) return -1;
+    if (!(a.in_slope >= 0.f && a.in_slope <= 1.f)) return -1;   // the producers' leaky ReLU is max(x, slope * x)
     const bool needs_v3 = (a.flags & (EPI_MASK_PRE | EPI_SPLIT | EPI_ACCUM2 | EPI_GATE)) != 0;
     int dev = 0;
     if (int rc = device_once(g_tc_once, &dev, [](int d) -> int {
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        B200_CUDA_OK(cudaFuncSetAttribute(tc3::conv1d_tc3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         for (int g : {2, 4})
-            for (int dl : {0, 1, 3, 5})
-                B200_CUDA_OK(cudaFuncSetAttribute(tc3::grouped_kernel(g, dl), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            B200_CUDA_OK(cudaFuncSetAttribute(tc3::grouped_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int* flag = nullptr;
         B200_CUDA_OK(cudaHostAlloc((void**)&flag, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         *flag = 0;
@@ -766,7 +767,7 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
         // grouped mode of the third-generation kernel: M = tap groups x channels, N = 256 time steps, 240 per tile
         const int G = L.tc_grp, J = (L.K + G - 1) / G;
         const int rp = (tc3::TT2 + (J - 1) * G * L.dil + 7) / 8 * 8;
-        if (rp <= 320 && tc3::smem_bytes3(rp, rp + 4) <= 227 * 1024) {
+        if (rp <= 320 && tc3::smem_bytes3(rp, rp + 4) + 128 + tc3::GROUP_XCHG_BYTES <= 227 * 1024) {
             tc3::Tc3Args t;
             memset(&t, 0, sizeof(t));
             t.x = a.x; t.x_bs = a.x_bs; t.x_cs = a.x_cs; t.Tin = a.Tin; t.in_slope = a.in_slope;
@@ -779,11 +780,13 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             t.rows_pad = rp; t.raw_w = rp + 4;
             t.B = io.B; t.n_ttiles = (a.Tq + t.tstep - 1) / t.tstep; t.n_rtiles = 1;
             t.err = g_tc_err;
-            size_t smemg = tc3::smem_bytes3(rp, rp + 4);
+            size_t smemg = (tc3::smem_bytes3(rp, rp + 4) + 127) / 128 * 128;
+            t.stage_off = (int)smemg;                          // partial-sum exchange tiles of the grouped epilogue
+            smemg += tc3::GROUP_XCHG_BYTES;
             set_ragged(t, a, smemg);
             const long long tiles = (long long)t.B * t.n_ttiles;
             const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-            B200_CUDA_OK(launch_tc3(tc3::grouped_kernel(G, L.dil), grid, smemg, st, t));
+            B200_CUDA_OK(launch_tc3(tc3::grouped_kernel(G), grid, smemg, st, t));
             count_launch();
             dispatch_note(DISPATCH_TC3_GROUPED);
             B200_CUDA_OK(cudaGetLastError());
@@ -821,10 +824,17 @@ static int try_launch_tc(const ConvLayer& L, const ConvIO& io, const ConvKArgs& 
             t.stage_off = (int)((smem3 + 15) / 16 * 16);
             smem3 = (size_t)t.stage_off + tc3::STAGE_BYTES;
         }
+        // plain layers (bias, residual, accumulate): the kernel with the lean epilogue; everything else (WaveNet gate / split,
+        // masks, ReLU, scale, final divide, transposed convs) the one with the general epilogue inline
+        const bool plain_epi = L.ups == 1 && !t.gate && t.split == 0 && !t.relu && !t.ymask && t.scale == 1.f && t.post_div == 1.f;
+        if (!t.stage && plain_epi && (smem3 + 127) / 128 * 128 + tc3::LEAN_STAGE_BYTES + tc3::ragged_table_bytes(t.B) <= 227 * 1024) {
+            t.stage_off = (int)((smem3 + 127) / 128 * 128);     // per-warp transposition tiles of the lean epilogue
+            smem3 = (size_t)t.stage_off + tc3::LEAN_STAGE_BYTES;
+        }
         set_ragged(t, a, smem3);
         const long long tiles = (long long)t.B * t.n_ttiles * t.n_rtiles;
         const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-        B200_CUDA_OK(launch_tc3(t.stage ? tc3::conv1d_tc3s_kernel : tc3::conv1d_tc3_kernel, grid, smem3, st, t));
+        B200_CUDA_OK(launch_tc3(t.stage ? tc3::conv1d_tc3s_kernel : plain_epi ? tc3::conv1d_tc3_kernel : tc3::conv1d_tc3x_kernel, grid, smem3, st, t));
         count_launch();
         dispatch_note(t.stage ? DISPATCH_TC3_STAGED : DISPATCH_TC3);
         B200_CUDA_OK(cudaGetLastError());

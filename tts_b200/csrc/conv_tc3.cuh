@@ -14,12 +14,12 @@
 //                                of the 256 columns), residual / accumulate loads as float4 with an order-enforced prefetch
 //
 // Grouped mode (GRP = 2 / 4) for narrow layers (exactly 64 / 32 output rows, the last two HiFiGAN stages): the 128
-// MMA rows are GRP tap-groups x (128/GRP) channels -- row (channel c, group g) carries the weights of taps g, g+GRP,
-// g+2*GRP, ... so one instruction stream of ceil(K/GRP) "tap blocks" (B shifted by GRP*dil rows per block) replaces K
-// of them and no MMA row is zero padding.  D_g[c, col] then still misses its own g*dil shift; the epilogue applies it
-// as a TMEM column offset (one tcgen05.ld per group), and sums the GRP partials, which live in adjacent lanes of one
-// warp, with a shuffle reduce-scatter.  Tiles advance by 240 columns so every shifted read stays inside the
-// 256-column accumulator.
+// MMA rows are GRP tap-groups x (128/GRP) channels -- row g * (128/GRP) + c carries the weights of channel c for taps
+// g, g+GRP, g+2*GRP, ... so one instruction stream of ceil(K/GRP) "tap blocks" (B shifted by GRP*dil rows per block)
+// replaces K of them and no MMA row is zero padding.  D_g[c, col] then still misses its own g*dil shift; a TMEM lane
+// quarter holds one group, so each epilogue warp applies the shift as the column offset of its tcgen05.ld and the four
+// warps of a column half sum their partials through a shared tile.  Tiles advance by 240 columns so every shifted read
+// stays inside the 256-column accumulator.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,6 +36,8 @@ using namespace tc;       // smem_u32, mbar_*, make_desc, make_idesc, mma_tf32, 
 constexpr int TT2 = 256;          // time steps per tile = MMA N
 constexpr int MROWS = 128;        // output rows per tile = MMA M (weight rows are zero padded up to it)
 constexpr int KC2 = 8;            // input channels per chunk (2 slabs, one MMA k-step)
+constexpr int RAWS = 324;         // raw (cp.async) row stride in floats: the widest window (320 slab rows + 4), a constant so
+                                  // that the transform's shared loads use immediate offsets
 #ifndef TC3_NRAW
 #define TC3_NRAW 4
 #endif
@@ -48,8 +50,17 @@ constexpr int KC2 = 8;            // input channels per chunk (2 slabs, one MMA 
 constexpr int NRAW = TC3_NRAW;    // raw (cp.async) ring depth
 constexpr int NA2 = TC3_NA2;      // transformed activation stages
 constexpr int NB2 = TC3_NB2;      // weight ring depth (one 8 KB tap block per slot)
-constexpr int NTHREADS2 = 448;    // warps 0-3 + 10-13 epilogue, 4-7 producers, 8 loader, 9 MMA
-constexpr int NPROD = 128;
+#ifndef TC3_RDEPTH
+#define TC3_RDEPTH 2
+#endif
+#ifndef TC3_NPW
+#define TC3_NPW 6
+#endif
+constexpr int NPW = TC3_NPW;      // producer warps.  r02: a producer warp spends ~400 dependent instructions per chunk (~2000
+                                  // cycles) and four of them paced every K <= 7 layer; eight halve the per-warp share
+constexpr int NPROD = 32 * NPW;
+constexpr int W_PROD = 4, W_LOAD = 4 + NPW, W_MMA = 5 + NPW, W_EPI2 = 6 + NPW;   // warp roles: 0-3 and W_EPI2..+3 epilogue
+constexpr int NTHREADS2 = 32 * (W_EPI2 + 4);
 
 struct Tc3Args {
     const float* x; long long x_bs; int x_cs; int Tin;
@@ -77,8 +88,9 @@ struct Tc3Args {
     int* err;
     unsigned long long* trace;  // optional [grid][32] globaltimer stamps (debug)
     int stage;                  // != 0: wide-layer epilogue goes through per-warp shared tiles (coalesced global access)
-    int stage_off;              // byte offset of those tiles in dynamic shared memory (8 warps x 5120 B)
-    int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA
+    int stage_off;              // byte offset of those tiles in dynamic shared memory (8 warps x 5120 B); grouped mode:
+                                // offset of the GROUP_XCHG_BYTES partial-sum exchange tiles
+    int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA, 32 epilogue = handshake only, 64 no test_wait probe, 128 lane = row lean epilogue
     // ---- ragged batches (null lens: every row spans the full tensor).  Row b only has tiles for GEMM columns below
     // min(Tq, lens[b] * rate_q + need_q) and its input is read as zero from min(Tin, lens[b] * rate_in + need_in) on:
     // padded frames cost nothing, and `need` keeps every sample below lens[b] bit-identical to the full computation
@@ -88,10 +100,14 @@ struct Tc3Args {
 };
 
 static inline size_t smem_bytes3(int rows_pad, int raw_w) {
-    return (size_t)NRAW * KC2 * raw_w * 4 + (size_t)NA2 * (4 * rows_pad * 16) + (size_t)NB2 * (4 * MROWS * 16) + 512;
+    (void)raw_w;     // raw rows are stored at the fixed stride RAWS
+    return (size_t)NRAW * KC2 * RAWS * 4 + (size_t)NA2 * (4 * rows_pad * 16) + (size_t)NB2 * (4 * MROWS * 16) + 512;
 }
 static inline size_t ragged_table_bytes(int B) { return ((size_t)(B + 1) * sizeof(int) + 15) / 16 * 16; }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -123,13 +139,361 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("ba
 constexpr int STAGE_BYTES = 8 * 5120;   // staged epilogue: per epilogue warp an output and a residual tile of [32][20] floats
 constexpr int TSTEP_GROUPED = 240;   // 15 chunks of 16 columns: leaves room for the (GRP-1)*dil <= 15 column shift
 
-template <int GRP, int DIL, bool STAGED = false>   // DIL > 0: the layer's dilation as a compile-time constant (grouped epilogue);
-                                                   // STAGED: wide-layer epilogue through per-warp shared tiles
+// Lean epilogue of one interior tile half (plain layers: bias, optional residual HR / accumulate HA): lane = one output row
+// (padding lanes were clamped to the last real row, so their loads are harmless and only their stores are predicated),
+// 128 columns in steps of NC.  HR / HA are compile-time so that every load is an UNCONDITIONAL definition: with `if (hr) ld`
+// ptxas kept the prefetched sets in local memory (store right after the load = wait for it), which serialised the steps
+// (r02 ncu source view: 86 % of the epilogue samples).  Software pipeline: the TMEM load and the residual / accumulate
+// loads of step g+1 fly while step g is finished.  Same operations in the same order as the general code (bit-identical).
+template <bool HR, bool HA>
+__device__ __forceinline__ void lean_rows(uint32_t dbase, float bias, const float* rp, float* yp, bool st_ok) {
+    constexpr int NC = 8;                      // columns per step (two float4 = one 32-byte sector per row)
+    uint32_t vA[NC], vB[NC];
+    float rA[NC], oA[NC], rB[NC], oB[NC];
+    auto pf = [&](int cg, float* r_, float* o_) {
+#pragma unroll
+        for (int j = 0; j < NC / 4; ++j) {
+            if constexpr (HR) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rp + cg + 4 * j));
+            if constexpr (HA) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yp + cg + 4 * j));
+        }
+    };
+    auto fin = [&](int cg, const uint32_t* v, const float* rv, const float* ov) {
+        float u[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            float t = __uint_as_float(v[i]) + bias;
+            if constexpr (HR) t += rv[i];
+            if constexpr (HA) t += ov[i];
+            u[i] = t;
+        }
+        if (st_ok) {
+#pragma unroll
+            for (int j = 0; j < NC / 4; ++j)
+                *reinterpret_cast<float4*>(yp + cg + 4 * j) = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+        }
+    };
+    pf(0, rA, oA);
+    tmem_ld_nowait<NC>(dbase, vA);
+#pragma unroll 1
+    for (int cg = 0; cg < 128; cg += 2 * NC) {
+        pf(cg + NC, rB, oB);
+        tmem_wait_ld();
+        tmem_ld_nowait<NC>(dbase + (uint32_t)(cg + NC), vB);
+        fin(cg, vA, rA, oA);
+        if (cg + 2 * NC < 128) pf(cg + 2 * NC, rA, oA);
+        tmem_wait_ld();
+        if (cg + 2 * NC < 128) tmem_ld_nowait<NC>(dbase + (uint32_t)(cg + 2 * NC), vA);
+        fin(cg + NC, vB, rB, oB);
+    }
+}
+
+// Lean epilogue, transposing variant (the default when its 20 KB of shared memory fit).  With lane = row every float4
+// LDG / STG of lean_rows touches 32 different 128-byte lines; r02 ablation: with the epilogue's global accesses switched
+// off the K = 3 layers ran 1.7x faster although the epilogue was not the pacing role -- its 32-wavefront instructions
+// stall the producers' copies in the shared LSU pipe.  Here a warp's 32 x 16 block goes through a private padded shared
+// tile once, so that lane (r8 = lane & 7, p4 = lane >> 3) owns float4 p4 of rows 8 i + r8: every global instruction covers
+// 8 rows x 64 contiguous bytes (4x fewer wavefronts, whole sectors), the residual / accumulate loads go straight to
+// registers in that mapping (no second tile).  ((acc + bias) + res) + old, as in the general code: bit-identical.
+constexpr int LEAN_TILE_FLOATS = 32 * 20;                 // per epilogue warp: [32 rows][16 + 4 pad] floats (conflict-free both ways)
+constexpr int LEAN_STAGE_BYTES = 8 * LEAN_TILE_FLOATS * 4;
+template <bool HR, bool HA>
+__device__ __forceinline__ void lean_rows_t(uint32_t dbase, float bias, float* tO, int lane, const float* rq, float* yq,
+                                            long long rcs, long long ycs, int row0, int Rows, bool do_st) {
+    const int r8 = lane & 7, p4 = lane >> 3;
+    const float* rrow[4];
+    float* yrow[4];
+    bool st_ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ri = row0 + 8 * i + r8, rci = ri < Rows ? ri : Rows - 1;       // padding rows: loads clamped, stores off
+        rrow[i] = rq + (long long)rci * rcs + 4 * p4;
+        yrow[i] = yq + (long long)rci * ycs + 4 * p4;
+        st_ok[i] = do_st && ri < Rows;
+    }
+    float* tw = tO + lane * 20;                          // lane = row view
+    const float* tr = tO + r8 * 20 + 4 * p4;             // (r8, p4) view, + i * 160
+    constexpr int D = TC3_RDEPTH;                        // residual register sets: loads run D - 1 column groups ahead
+    float r0[16], r1[16], r2[D == 4 ? 16 : 1], r3[D == 4 ? 16 : 1];
+    static_assert(D == 2 || D == 4, "TC3_RDEPTH must be 2 or 4");
+    auto pf = [&](int cg, float* r_) {
+        if constexpr (HR) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * i]), "=f"(r_[4 * i + 1]), "=f"(r_[4 * i + 2]), "=f"(r_[4 * i + 3]) : "l"(rrow[i] + cg));
+        }
+    };
+    auto group = [&](int cg, const float* rv, float* rn) {
+        float o[16];
+        if (cg + 16 * (D - 1) < 128) pf(cg + 16 * (D - 1), rn);
+        if constexpr (HA) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[4 * i]), "=f"(o[4 * i + 1]), "=f"(o[4 * i + 2]), "=f"(o[4 * i + 3]) : "l"(yrow[i] + cg));
+        }
+        uint32_t v[16];
+        tmem_ld16_nowait(dbase + (uint32_t)cg, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(tw + 4 * j) = make_float4(__uint_as_float(v[4 * j]) + bias, __uint_as_float(v[4 * j + 1]) + bias,
+                                                                 __uint_as_float(v[4 * j + 2]) + bias, __uint_as_float(v[4 * j + 3]) + bias);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 t = *reinterpret_cast<const float4*>(tr + i * 160);
+            if constexpr (HR) { t.x += rv[4 * i]; t.y += rv[4 * i + 1]; t.z += rv[4 * i + 2]; t.w += rv[4 * i + 3]; }
+            if constexpr (HA) { t.x += o[4 * i]; t.y += o[4 * i + 1]; t.z += o[4 * i + 2]; t.w += o[4 * i + 3]; }
+            if (st_ok[i]) *reinterpret_cast<float4*>(yrow[i] + cg) = t;
+        }
+        __syncwarp();
+    };
+    if constexpr (D == 2) {
+        pf(0, r0);
+#pragma unroll 1
+        for (int cg = 0; cg < 128; cg += 32) {
+            group(cg, r0, r1);
+            group(cg + 16, r1, r0);
+        }
+    } else {
+        pf(0, r0); pf(16, r1); pf(32, r2);
+#pragma unroll 1
+        for (int cg = 0; cg < 128; cg += 64) {
+            group(cg, r0, r3);
+            group(cg + 16, r1, r0);
+            group(cg + 32, r2, r1);
+            group(cg + 48, r3, r2);
+        }
+    }
+}
+
+// Everything the lean epilogue does not cover (WaveNet gate / res-skip split, masks, ReLU, scale, final divide, polyphase
+// stores of the transposed convs, edge tiles): one tile half per call.  Deliberately NOT inlined: inside the tile loop its
+// loop invariants were hoisted across the lean path and pushed that path's prefetched values out of registers.
+template <bool STAGED>
+__device__ __forceinline__ void general_tile_body(const Tc3Args& a, unsigned char* smem, uint32_t tmem_base, uint32_t acc_cols,
+                                                  int b, int rt, int q0, int buf, int lq, int half, int lane, int warp) {
+    const int ups = a.ups;
+    const int r = rt * MROWS + lq * 32 + lane;             // GEMM row of this lane
+    const bool rok = r < a.Rows;
+    const int rc = rok ? r : a.Rows - 1;
+    const uint32_t dbase = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 128);
+    const int qb = q0 + half * 128;
+    float bias = a.bias[rc];
+    if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + rc);
+    if (a.gate) {
+        // WaveNet gate (wavenet.py:6-13): even lane = tanh argument, odd lane = sigmoid argument of row r/2
+        float* yrow = a.y + (long long)b * a.y_bs + (long long)(rc >> 1) * a.y_cs;
+        const bool vec_ok = ((a.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0);
+        const bool even = (lane & 1) == 0;
+        for (int cg = 0; cg < 128; cg += 16) {
+            float v[16];
+            tmem_ld16(dbase + (uint32_t)cg, v);
+            const int q = qb + cg;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float u = v[i] + bias;
+                const float act = even ? tanhf(u) : 1.f / (1.f + expf(-u));
+                const float other = __shfl_xor_sync(0xffffffffu, act, 1);
+                v[i] = act * other;
+            }
+            if (rok && even) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int qq = q + 4 * j;
+                    if (vec_ok && qq + 3 < a.Tout) *reinterpret_cast<float4*>(yrow + qq) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = v[4 * j + e];
+                    }
+                }
+            }
+        }
+    } else if (STAGED && ups == 1 && a.stage && a.split == 0 && qb + 128 <= a.Tout && ((a.y_cs | a.y_bs) & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
+               (!a.res || ((((a.res_cs | a.res_bs) & 3) == 0) && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0))) {
+        // ---- staged epilogue (interior tiles of wide layers).  With lane = row every float4 LDG / STG of the
+        // direct path touches 32 different cache lines; measured, that L1 wavefront time is not hidden
+        // (profiles/r01_tc_grouped_notes.md).  Here each warp transposes its 32 x 16 block through a private
+        // shared tile: global accesses are 8 rows x 64 contiguous bytes per instruction (4x fewer wavefronts),
+        // the residual arrives by cp.async one column group ahead.
+        const int ew = (warp < 4) ? warp : warp - W_EPI2 + 4;                       // epilogue warp 0..7
+        float* tO = reinterpret_cast<float*>(smem + a.stage_off) + ew * 1280;   // [32][20]
+        float* tR = tO + 640;
+        const int r8 = lane & 7, p4 = lane >> 3;
+        const int Rbase = rt * MROWS + lq * 32 + r8;                        // + 8*i
+        float* ybase = a.y + (long long)b * a.y_bs + (long long)Rbase * a.y_cs + qb + 4 * p4;
+        const float* rbase = (a.res && !(a.dbg & 4)) ? a.res + (long long)b * a.res_bs + (long long)Rbase * a.res_cs + qb + 4 * p4 : nullptr;
+        const bool acc_r = a.accum != 0 && !(a.dbg & 4), mpost_r = a.mask_post != 0, do_store = !(a.dbg & 8);
+        const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
+        float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;   // lane = row view (accumulate loads)
+        auto issue_res = [&](int cg) {
+            if (!rbase) return;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (Rbase + 8 * i < a.Rows)
+                    cp_async16_zfill(smem_u32(tR + (8 * i + r8) * 20 + 4 * p4), rbase + (long long)(8 * i) * a.res_cs + cg, 16u);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto prefetch_acc = [&](int cg, float* o_) {
+            if (!acc_r || !rok) return;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qb + cg + 4 * j));
+        };
+        issue_res(0);
+#pragma unroll 1
+        for (int cg = 0; cg < 128; cg += 16) {
+            float v[16], ov[16], rv[16];
+            prefetch_acc(cg, ov);           // accumulate-into-destination (two layers per stage): same-group load
+            if (rbase) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(tR + lane * 20 + 4 * j);
+                    rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w;
+                }
+                __syncwarp();
+                if (cg + 16 < 128) issue_res(cg + 16);
+            }
+            tmem_ld16(dbase + (uint32_t)cg, v);
+            const int q = qb + cg;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float u = v[i] + bias;
+                if (a.relu) u = fmaxf(u, 0.f);
+                const float mk = mrow ? __ldg(mrow + q + i) : 1.f;
+                if (a.mask_pre) u *= mk;
+                if (rbase) u += rv[i];
+                u *= a.scale;
+                if (acc_r) u += ov[i];
+                if (a.post_div != 1.f) u = u / a.post_div;
+                if (mpost_r) u *= mk;
+                v[i] = u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(tO + lane * 20 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 o4 = *reinterpret_cast<const float4*>(tO + (8 * i + r8) * 20 + 4 * p4);
+                if (do_store && Rbase + 8 * i < a.Rows) *reinterpret_cast<float4*>(ybase + (long long)(8 * i) * a.y_cs + cg) = o4;
+            }
+            __syncwarp();
+        }
+    } else if (ups == 1) {
+        float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;
+        bool acc_r = a.accum != 0, mpost_r = a.mask_post != 0;
+        if (a.split > 0) {          // WaveNet res/skip rows (wavenet.py:108-113)
+            if (rc < a.split) { acc_r = true; mpost_r = true; }
+            else { yrow = a.y2 + (long long)b * a.y2_bs + (long long)(rc - a.split) * a.y2_cs; acc_r = a.accum2 != 0; mpost_r = false; }
+        }
+        const float* rrow = a.res ? a.res + (long long)b * a.res_bs + (long long)rc * a.res_cs : nullptr;
+        const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
+        const int ycs_eff = (a.split > 0 && rc >= a.split) ? a.y2_cs : a.y_cs;
+        const bool vec_ok = ((ycs_eff & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
+                            (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+        // order-enforced software pipeline: the (volatile) loads of group j+1 are issued before the (volatile)
+        // TMEM load of group j, into the OTHER of two register sets -- never copied (a move of a pending load's
+        // result waits for the load and would serialise the groups).  float4 per lane along time (lane = one row).
+        float rA[16], oA[16], rB[16], oB[16];
+        auto prefetch = [&](int cg, float* r_, float* o_) {
+            const int q = qb + cg;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int qq = q + 4 * j;
+                if (vec_ok && qq + 3 < a.Tout) {
+                    if (rrow) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rrow + qq));
+                    if (acc_r) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int qe = min(qq + e, a.Tout - 1);
+                        if (rrow) asm volatile("ld.global.f32 %0, [%1];" : "=f"(r_[4 * j + e]) : "l"(rrow + qe));
+                        if (acc_r) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
+                    }
+                }
+            }
+        };
+        const bool ld_ok = rok && !(a.dbg & 4), st_ok = rok && !(a.dbg & 8);
+        auto group = [&](int cg, const float* rv, const float* ov, float* rn, float* on) {
+            float v[16];
+            if (ld_ok && cg + 16 < 128) prefetch(cg + 16, rn, on);
+            tmem_ld16(dbase + (uint32_t)cg, v);
+            const int q = qb + cg;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float u = v[i] + bias;
+                if (a.relu) u = fmaxf(u, 0.f);
+                const float mk = mrow ? __ldg(mrow + min(q + i, a.Tout - 1)) : 1.f;
+                if (a.mask_pre) u *= mk;
+                if (a.res) u += rv[i];
+                u *= a.scale;
+                if (acc_r) u += ov[i];
+                if (a.post_div != 1.f) u = u / a.post_div;
+                if (mpost_r) u *= mk;
+                v[i] = u;
+            }
+            if (st_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int qq = q + 4 * j;
+                    if (vec_ok && qq + 3 < a.Tout) {
+                        *reinterpret_cast<float4*>(yrow + qq) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = v[4 * j + e];
+                    }
+                }
+            }
+        };
+        if (ld_ok) prefetch(0, rA, oA);
+#pragma unroll 1
+        for (int cg = 0; cg < 128; cg += 32) {
+            group(cg, rA, oA, rB, oB);
+            group(cg + 16, rB, oB, rA, oA);
+        }
+    } else {
+        // polyphase store: row r = co*ups + ph, column q -> y[co][q*ups + ph]; a warp's 32 lanes cover whole
+        // groups of `ups` phases, i.e. contiguous runs of `ups` output samples per channel
+        const int co = rc / ups, ph = rc - co * ups;
+        float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs + ph;
+        for (int cg = 0; cg < 128; cg += 16) {
+            float v[16];
+            tmem_ld16(dbase + (uint32_t)cg, v);
+            if (!rok) continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int q = qb + cg + i;
+                float u = v[i] + bias;
+                if (a.relu) u = fmaxf(u, 0.f);
+                const long long t = (long long)q * ups;
+                if (q < a.Tq && t + ph < a.Tout) yrow[t] = u;
+            }
+        }
+    }
+}
+
+// Out-of-line call of the general epilogue for the kernels whose hot path is the lean one (edge tiles only): inlined into
+// their tile loop its loop invariants were hoisted across the lean path.  One copy of the arguments per call: through
+// the reference every field use would be a generic load.
+template <bool STAGED>
+__device__ __noinline__ void general_tile_call(const Tc3Args& a_ref, unsigned char* smem, uint32_t tmem_base, uint32_t acc_cols,
+                                               int b, int rt, int q0, int buf, int lq, int half, int lane, int warp) {
+    const Tc3Args a = a_ref;
+    general_tile_body<STAGED>(a, smem, tmem_base, acc_cols, b, rt, q0, buf, lq, half, lane, warp);
+}
+
+template <int GRP, bool STAGED = false, bool LEAN = true>   // GRP: tap groups stacked in the 128 MMA rows (1 = plain); STAGED: wide-layer
+                                          // epilogue through per-warp shared tiles; LEAN: plain-layer kernel (lean epilogue inline, general
+                                          // one out of line) -- false for the WaveNet / masked / transposed layers (general epilogue inline)
 __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ROWS = a.rows_pad, RAWW = a.raw_w, K = a.KJ;
-    const uint32_t rawStage = (uint32_t)KC2 * RAWW * 4;
+    const uint32_t rawStage = (uint32_t)KC2 * RAWS * 4;
     const uint32_t slabA = (uint32_t)ROWS * 16, stageA = 4 * slabA;     // hi[2] + lo[2]
     const uint32_t slabB = (uint32_t)MROWS * 16, stageB = 4 * slabB;   // one tap block: {hi,lo}[2 slabs][128 rows][16 B]
     unsigned char* smRaw = smem;
@@ -178,7 +542,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(ACC_FULL + i), 1); mbar_init(BAR(ACC_EMPTY + i), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -191,7 +555,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     // griddepcontrol.wait); every role that touches activations waits for the previous layer here.  The weight loader
     // (warp 8) reads only constants and starts filling its ring at once.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp != 8) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (warp != W_LOAD) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     auto decode = [&](int it, int& b, int& rt, int& q0) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -215,65 +579,82 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         return (int)(e < (long long)a.Tin ? (e > 0 ? e : 0) : (long long)a.Tin);
     };
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= W_PROD && warp < W_PROD + NPW) {
         // ============================================================ producers
-        const int ptid = tid - 128;
+        const int ptid = tid - 32 * W_PROD;
         const int total = my_tiles * nchunks;
         const int vec_per_row = RAWW / 4;
         const int nvec = KC2 * vec_per_row;
         const float slope = a.in_slope;
+        const float* const xg = a.x;
+        const long long x_bs = a.x_bs;
+        const int x_cs = a.x_cs, Cin = a.Cin, pad = a.pad;
+        const bool tracing = a.trace != nullptr;
         bool ok = true;
-        // per-thread work items are the same for every chunk: decode them once (no divisions in the loop)
-        constexpr int MAXV = 6, MAXI = 5;          // ceil(8*81/128), ceil(2*320/128)
-        int v_off[MAXV], v_ch[MAXV], v_t[MAXV];    // raw smem float offset, channel in chunk, time offset from `tal`
+        // This loop paces every K <= 7 layer (r02 ncu source view: ~400 dependent instructions per warp and chunk, most of
+        // them address arithmetic and bounds logic, ~2000 cycles).  So: per-thread work items are decoded ONCE (no
+        // divisions in the loop), the raw row stride is a compile-time constant (shared loads take immediate offsets),
+        // interior windows take a copy path without any bounds logic, and leaky ReLU is max(x, slope * x).
+        constexpr int MAXV = (8 * 81 + NPROD - 1) / NPROD, MAXI = (2 * 320 + NPROD - 1) / NPROD;   // raw vectors / slab rows per thread
+        int v_ch[MAXV], v_t[MAXV], v_src[MAXV];    // channel in chunk (-1: none), time offset from `tal`, global float offset
+        uint32_t v_dst[MAXV];                      // byte offset in a raw stage
 #pragma unroll
         for (int e = 0; e < MAXV; ++e) {
             const int v = ptid + e * NPROD;
             const int ch = v / vec_per_row, j = v - ch * vec_per_row;
             v_ch[e] = (v < nvec) ? ch : -1;
             v_t[e] = 4 * j;
-            v_off[e] = ch * RAWW + 4 * j;
+            v_src[e] = ch * x_cs + 4 * j;
+            v_dst[e] = (uint32_t)(ch * RAWS + 4 * j) * 4u;
         }
-        int i_raw[MAXI], i_dst[MAXI];              // raw float offset of channel 0 of the slab, slab byte offset
+        int i_raw[MAXI], i_dst[MAXI];              // raw float offset of channel 0 of the slab row (-1: none), slab byte offset
 #pragma unroll
         for (int e = 0; e < MAXI; ++e) {
             const int idx = ptid + e * NPROD;
             const int sl = idx / ROWS, r = idx - sl * ROWS;
-            i_raw[e] = (idx < 2 * ROWS) ? (4 * sl) * RAWW + r : -1;
+            i_raw[e] = (idx < 2 * ROWS) ? (4 * sl) * RAWS + r : -1;
             i_dst[e] = (int)(sl * slabA) + r * 16;
         }
-        // running positions instead of divisions / modulos per chunk (this loop is on the critical path of the K <= 7 layers)
-        int iss_it = 0, iss_c = 0, iss_ring = 0, iss_b = 0, iss_q0 = 0, iss_Tin = 0;   // cp.async front: tile, chunk, raw slot
-        bool iss_new = true;
+        // running positions instead of divisions / modulos per chunk
+        int iss_it = 0, iss_c = 0, iss_ring = 0, iss_tal = 0, iss_Tin = 0;             // cp.async front: tile, chunk, raw slot
+        const float* iss_row = xg;
+        bool iss_new = true, iss_int = false;
         int tr_it = 0, tr_c = 0, tr_ring = 0, tr_q0 = 0, as = 0;                       // transform: tile, chunk, raw slot, A stage
         uint32_t pa_empty = 1;                                    // parity to wait for on A_EMPTY[as]: round 1 -> 0, round 2 -> 1, ...
         bool tr_new = true;
         const bool no_cp = (a.dbg & 1) != 0;
+        const uint32_t raw_u32 = smem_u32(smRaw);
         auto issue = [&](int g) {
             if (g < total && !no_cp) {
                 if (iss_new) {
-                    int rt_;
-                    decode(iss_it, iss_b, rt_, iss_q0);
-                    iss_Tin = input_extent(iss_b);
+                    int b_, rt_, q0_;
+                    decode(iss_it, b_, rt_, q0_);
+                    iss_Tin = input_extent(b_);
+                    iss_tal = (q0_ - pad) & ~3;                            // 16-byte aligned window start (may be < 0)
+                    iss_row = xg + (long long)b_ * x_bs;
+                    iss_int = iss_tal >= 0 && iss_tal + RAWW <= iss_Tin && (Cin & (KC2 - 1)) == 0;
                     iss_new = false;
                 }
-                const int c = iss_c;
-                const int b = iss_b, q0 = iss_q0, Tin_b = iss_Tin;
-                const int tal = ((q0 - a.pad) & ~3);                     // 16-byte aligned window start (may be < 0)
-                const float* xb = a.x + (long long)b * a.x_bs;
-                const uint32_t dst0 = smem_u32(smRaw + iss_ring * rawStage);
+                const uint32_t dst0 = raw_u32 + (uint32_t)iss_ring * rawStage;
+                if (iss_int) {                                             // whole window inside the row: plain 16-byte copies
+                    const float* src = iss_row + (long long)(iss_c * KC2) * x_cs + iss_tal;
 #pragma unroll
-                for (int e = 0; e < MAXV; ++e) {
-                    if (v_ch[e] < 0) continue;
-                    const int t = tal + v_t[e];
-                    const int cg = c * KC2 + v_ch[e];
-                    // t is a multiple of 4, so a vector is either wholly before the sequence start (zero fill),
-                    // wholly inside, or cut by its end (partial source size, rest zero-filled by the hardware)
-                    int nb = 0;
-                    if (cg < a.Cin && t >= 0) nb = 4 * max(0, min(4, Tin_b - t));
-                    const int tsafe = (t >= 0 && t < Tin_b) ? t : 0;
-                    const float* src = xb + (long long)(cg < a.Cin ? cg : 0) * a.x_cs + tsafe;
-                    cp_async16_zfill(dst0 + (uint32_t)v_off[e] * 4u, src, (uint32_t)nb);
+                    for (int e = 0; e < MAXV; ++e)
+                        if (v_ch[e] >= 0) cp_async16(dst0 + v_dst[e], src + v_src[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < MAXV; ++e) {
+                        if (v_ch[e] < 0) continue;
+                        const int t = iss_tal + v_t[e];
+                        const int cg = iss_c * KC2 + v_ch[e];
+                        // t is a multiple of 4, so a vector is either wholly before the sequence start (zero fill),
+                        // wholly inside, or cut by its end (partial source size, rest zero-filled by the hardware)
+                        int nb = 0;
+                        if (cg < Cin && t >= 0) nb = 4 * max(0, min(4, iss_Tin - t));
+                        const int tsafe = (t >= 0 && t < iss_Tin) ? t : 0;
+                        const float* src = iss_row + (long long)(cg < Cin ? cg : 0) * x_cs + tsafe;
+                        cp_async16_zfill(dst0 + v_dst[e], src, (uint32_t)nb);
+                    }
                 }
                 if (++iss_c == nchunks) { iss_c = 0; ++iss_it; iss_new = true; }
             }
@@ -292,34 +673,32 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 decode(tr_it, b_, rt_, tr_q0);
                 tr_new = false;
             }
-            const int q0 = tr_q0;
-            const int tin0 = q0 - a.pad, off = tin0 - (tin0 & ~3);
+            const int tin0 = tr_q0 - pad, off = tin0 - (tin0 & ~3);
             const float* raw = reinterpret_cast<const float*>(smRaw + tr_ring * rawStage) + off;
             unsigned char* base = smA + as * stageA;
-            float u[MAXI][4];
             if (!(a.dbg & 2)) {
+                float u[MAXI][4];
 #pragma unroll
-            for (int e = 0; e < MAXI; ++e) {           // all shared loads first ...
-                const int o = i_raw[e] < 0 ? 0 : i_raw[e];
+                for (int e = 0; e < MAXI; ++e) {           // all shared loads first ...
+                    const float* rp = raw + (i_raw[e] < 0 ? 0 : i_raw[e]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) u[e][i] = raw[o + i * RAWW];
-            }
-#pragma unroll
-            for (int e = 0; e < MAXI; ++e) {           // ... then prologue, hi/lo split and the two 16-byte stores
-                if (i_raw[e] < 0) continue;
-                float4 hi, lo;
-                float* ph = &hi.x; float* pl = &lo.x;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float w_ = u[e][i];
-                    w_ = w_ > 0.f ? w_ : w_ * slope;
-                    const float h = __uint_as_float(__float_as_uint(w_) & 0xFFFFE000u);
-                    ph[i] = h;
-                    pl[i] = w_ - h;
+                    for (int i = 0; i < 4; ++i) u[e][i] = rp[i * RAWS];
                 }
-                *reinterpret_cast<float4*>(base + i_dst[e]) = hi;
-                *reinterpret_cast<float4*>(base + 2 * slabA + i_dst[e]) = lo;
-            }
+#pragma unroll
+                for (int e = 0; e < MAXI; ++e) {           // ... then prologue, hi/lo split and the two 16-byte stores
+                    if (i_raw[e] < 0) continue;
+                    float4 hi, lo;
+                    float* ph = &hi.x; float* pl = &lo.x;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float w_ = fmaxf(u[e][i], u[e][i] * slope);        // leaky ReLU for 0 <= slope <= 1 (1: identity)
+                        const float h = __uint_as_float(__float_as_uint(w_) & 0xFFFFE000u);
+                        ph[i] = h;
+                        pl[i] = w_ - h;
+                    }
+                    *reinterpret_cast<float4*>(base + i_dst[e]) = hi;
+                    *reinterpret_cast<float4*>(base + 2 * slabA + i_dst[e]) = lo;
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -327,11 +706,11 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             if (++tr_c == nchunks) { tr_c = 0; ++tr_it; tr_new = true; }
             if (++tr_ring == NRAW) tr_ring = 0;
             if (++as == NA2) { as = 0; pa_empty ^= 1u; }
-            if (ptid == 0) { if (g == 0) TC3_STAMP(1); if (g == nchunks - 1) TC3_STAMP(2); if (g == 2 * nchunks - 1) TC3_STAMP(3); if (g == 4 * nchunks - 1) TC3_STAMP(4); }
+            if (tracing && ptid == 0) { if (g == 0) TC3_STAMP(1); if (g == nchunks - 1) TC3_STAMP(2); if (g == 2 * nchunks - 1) TC3_STAMP(3); if (g == 4 * nchunks - 1) TC3_STAMP(4); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (ptid == 0) TC3_STAMP(5);
-    } else if (warp == 8) {
+    } else if (warp == W_LOAD) {
         // ============================================================ weight loader
         // One lane per ring slot: lane s owns slot s and feeds it with tap blocks s, s + NB2, s + 2*NB2, ... of this CTA's
         // block sequence.  A single thread walking the ring paid its wait -> expect_tx -> bulk-copy chain (~400 cycles) once
@@ -365,7 +744,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // ============================================================ MMA issuer
         // ncu (profiles/r02_tc3_issue_loop.md): this ONE thread is what bounds the MMA-heavy layers -- it never waits long
         // on a barrier, its own dependent instruction chain took ~710 cycles per tap against the 384 cycles the three MMAs
@@ -385,6 +764,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             const uint64_t wdesc0 = make_desc(smem_u32(smB), slabB);
             const uint32_t bfull0 = BAR(B_FULL), bempty0 = BAR(B_EMPTY);
             const bool no_mma = (a.dbg & 16) != 0;
+            const bool no_probe = (a.dbg & 64) != 0;                                       // every weight barrier through try_wait
             bool ok = true;
             int sa = 0; uint32_t pa = 0;                                                  // activation stage / its parity
             int sb = 0; uint32_t pb = 0;                                                  // weight slot / its parity
@@ -412,7 +792,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         // where the NEXT tap's weights will be; peek at their barrier now (result used next iteration)
                         const bool wrap = (sb == NB2 - 1);
                         const uint32_t nfull = wrap ? bfull0 : bfull + 8u, npb = wrap ? (pb ^ 1u) : pb;
-                        const bool have_next = mbar_test(nfull, npb);
+                        const bool have_next = no_probe ? false : mbar_test(nfull, npb);
                         const uint64_t w_hi = wdesc, w_lo = wdesc + wlo_off;
                         if (leader) {
                             if (!no_mma) {
@@ -443,17 +823,24 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         bool ok = true;
         const int ups = a.ups;
         const int lq = warp & 3;                     // TMEM lane quarter this warp may access
-        const int half = (warp >= 10) ? 1 : 0;       // warps 0-3: columns [0,128), warps 10-13: [128,256)
+        const int half = (warp >= W_EPI2) ? 1 : 0;   // warps 0-3: columns [0,128), warps W_EPI2..+3: [128,256)
         if constexpr (GRP > 1) {
-            // ---- grouped epilogue: lane = (channel cc, tap group g); out[c, t] = sum_g D_g[c, t + g*dil]
-            // Written for instruction count and a small footprint (profiles/r01_tc_grouped_notes.md): one TMEM window per
-            // 16 columns, the per-lane shift folded into the reduce-scatter's selects, residual loads two groups ahead.
-            // (Unrolling the eight groups of a tile to prefetch a whole tile ahead thrashed the instruction cache.)
-                        constexpr int CPW = 32 / GRP, NV = 16 / GRP;
-            const int g = lane & (GRP - 1), cc = lane / GRP;
-            const bool g0 = (g & 1) != 0, g1 = (g & 2) != 0;
-            const int co = lq * CPW + cc;                                   // Rows == 128 / GRP
-            const int coff = (GRP == 4) ? ((g & 1) * 8 + (g >> 1) * 4) : g * 8;   // this lane's columns in a group
+            // ---- grouped epilogue: out[c, t] = sum_g D_g[c, t + g*dil].  MMA row m = g * CH + c (CH = 128 / GRP channels), so a
+            // warp's TMEM lane quarter holds ONE tap group (GRP = 4) or half of one (GRP = 2) and applies that group's shift as
+            // a plain column offset of its tcgen05.ld -- no per-lane selects.  The GRP partials of a channel live in different
+            // warps; the four warps of a column half exchange them through a double-buffered shared tile (one named barrier
+            // per 16-column group), after which thread (c, j) owns float4 j of channel c: 4 lanes = 64 contiguous bytes.
+            // r02 measurement behind this (profiles/r02_epilogue_instruction_bound.md): the previous shuffle reduce-scatter
+            // cost ~180 instructions per lane and 16 columns and paced the narrow layers (3.3 us per tile with no memory ops).
+            constexpr int CH = 128 / GRP;              // output channels
+            constexpr int NQ = CH / 32;                // float4 per thread and 16-column group (1 or 2)
+            constexpr int NV = 4 * NQ;
+            const int tq = lq * 32 + lane;             // thread within the half's four warps == its TMEM row
+            const int gq = (lq * 32) / CH;             // tap group of this warp's TMEM lanes
+            const int cw = tq - gq * CH;               // channel of this lane's TMEM row
+            const int co = (tq * NQ) >> 2;             // channel this thread finishes
+            const int j0 = (tq & (4 / NQ - 1)) * NQ;   // its first float4 within a 16-column group
+            const int coff = 4 * j0;
             const int cbeg = half ? 128 : 0;
             const bool has_res = a.res != nullptr && !(a.dbg & 4);
             const bool acc_r = a.accum != 0 && !(a.dbg & 4);
@@ -461,11 +848,17 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                                 (!a.res || (((a.res_cs & 3) == 0) && ((a.res_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0)));
             const bool relu = a.relu != 0, do_store = !(a.dbg & 8);
             const float scale = a.scale, post_div = a.post_div;
+            const bool plain = !relu && scale == 1.f;
+            float* xq = reinterpret_cast<float*>(smem + a.stage_off) + half * 4096;        // two buffers of [128 rows][16] floats
+            const int wsw = (cw >> 1) & 3, rsw = (co >> 1) & 3;                             // 16-byte unit swizzle (bank spread)
+            float* xw = xq + tq * 16;
+            const uint32_t gshift = (uint32_t)(gq * a.dil);
+            const int bar_id = 2 + half;
+            int xbuf = 0;
             bool fast = false;                                            // interior tile: no bounds checks at all
             auto prefetch_any = [&](const float* rr, int q, float* dst) {   // values of one column group of a row -> registers
-
 #pragma unroll
-                for (int j = 0; j < NV / 4; ++j) {
+                for (int j = 0; j < NQ; ++j) {
                     const int qq = q + 4 * j;
                     if (fast || (vec_ok && qq + 3 < a.Tout)) {
                         asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dst[4 * j]), "=f"(dst[4 * j + 1]), "=f"(dst[4 * j + 2]), "=f"(dst[4 * j + 3]) : "l"(rr + qq));
@@ -485,8 +878,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 const int cend = half ? a.tstep : min(128, a.tstep);
                 fast = vec_ok && (q0 + a.tstep <= a.Tout);
                 // Residual / accumulate values are prefetched TWO column groups ahead into three rotating register sets that
-                // are never copied: a register move of a pending load's result waits for the load, which made every group
-                // pay a full memory latency (r02 timeline: ~1.5 k cycles per 16-column group, the narrow stages' bound).
+                // are never copied (a register move of a pending load's result waits for the load).
                 float rA[NV], rB[NV], rC[NV], oA[NV], oB[NV], oC[NV];
                 float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs;
                 const float* orow = acc_r ? yrow : nullptr;
@@ -498,85 +890,71 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 if (!ok) break;
                 tc_fence_after();
                 if (tid == 0) { if (it == 0) TC3_STAMP(16); if (it == 1) TC3_STAMP(18); if (it == 3) TC3_STAMP(20); }
-                const uint32_t dlane = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16);
+                if (a.dbg & 32) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf)); continue; }   // probe: handshake only
+                const uint32_t dlane = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16) + gshift;
                 float bias = a.bias[co];
                 if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + co);
+                uint32_t P[16];
+                tmem_ld16_nowait(dlane + (uint32_t)cbeg, P);                 // this warp's partial of the first column group
                 auto group = [&](int cg, const float* rv, const float* ov, float* rf, float* of) {
                     if (cg + 32 < cend) { prefetch(rrow, q0 + cg + 32 + coff, rf); prefetch_acc(orow, q0 + cg + 32 + coff, of); }
-                    {
-                    float S[8];
-                    const int q = q0 + cg + coff;
-                    if constexpr (DIL > 0) {
-                        // TMEM reads run at ~64 B/clk per SM: one window [cg, cg + 16 + (GRP-1)*DIL) serves all
-                        // groups.  Lane (c, g) needs P[i] = w[i + g*DIL]; the first reduce-scatter step sends
-                        // P[i] or P[i+8] and keeps the other, so the g0 half of the shift is folded into those selects
-                        constexpr int EXT = (GRP - 1) * DIL;
-                        constexpr int EXTN = EXT <= 1 ? 1 : EXT <= 2 ? 2 : EXT <= 4 ? 4 : EXT <= 8 ? 8 : 16;
-                        static_assert(EXT <= 16, "grouped epilogue: shift window too wide");
-                        uint32_t w[16 + EXTN];
-                        tmem_ld_nowait<16>(dlane + (uint32_t)cg, w);
-                        tmem_ld_nowait<EXTN>(dlane + (uint32_t)(cg + 16), w + 16);
-                        tmem_wait_ld();
-                        if constexpr (GRP == 4) {
+                    float* xb = xw + xbuf * 2048;
+                    tmem_wait_ld();
 #pragma unroll
-                            for (int i = 0; i < 16 + DIL; ++i) w[i] = g1 ? w[i + 2 * DIL] : w[i];   // t[i] = w[i + 2*g1*DIL]
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float send = __uint_as_float(g0 ? w[i + DIL] : w[i + 8]);
-                            const float keep = __uint_as_float(g0 ? w[i + 8 + DIL] : w[i]);
-                            S[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                        }
-                    } else {
-                        float P[16];
-                        uint32_t l0[16], l1[16];
-                        tmem_ld16_nowait(dlane + (uint32_t)cg, l0);
-                        tmem_ld16_nowait(dlane + (uint32_t)(cg + a.dil), l1);
-                        if constexpr (GRP == 4) {
-                            uint32_t l2[16], l3[16];
-                            tmem_ld16_nowait(dlane + (uint32_t)(cg + 2 * a.dil), l2);
-                            tmem_ld16_nowait(dlane + (uint32_t)(cg + 3 * a.dil), l3);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const uint32_t lo2 = g0 ? l1[i] : l0[i], hi2 = g0 ? l3[i] : l2[i];
-                                P[i] = __uint_as_float(g1 ? hi2 : lo2);
-                            }
-                        } else {
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) P[i] = __uint_as_float(g0 ? l1[i] : l0[i]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float send = g0 ? P[i] : P[i + 8];
-                            S[i] = (g0 ? P[i + 8] : P[i]) + __shfl_xor_sync(0xffffffffu, send, 1);
-                        }
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(xb + 4 * (j ^ wsw)) = make_uint4(P[4 * j], P[4 * j + 1], P[4 * j + 2], P[4 * j + 3]);
+                    if (cg + 16 < cend) tmem_ld16_nowait(dlane + (uint32_t)(cg + 16), P);   // next group's partial flies during the exchange
+                    else {                                                                   // last TMEM read of this tile: release the accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
                     }
+                    named_bar_sync(bar_id, 128);
+                    const float* xr = xq + xbuf * 2048 + co * 16;
+                    xbuf ^= 1;
                     float R[NV];
-                    if constexpr (GRP == 4) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float send = g1 ? S[i] : S[i + 4];
-                            R[i] = (g1 ? S[i + 4] : S[i]) + __shfl_xor_sync(0xffffffffu, send, 2);
+                    for (int e = 0; e < NQ; ++e) {
+                        const int u4 = 4 * ((j0 + e) ^ rsw);
+                        const float4 p0 = *reinterpret_cast<const float4*>(xr + u4);
+                        const float4 p1 = *reinterpret_cast<const float4*>(xr + CH * 16 + u4);
+                        float4 s = make_float4(p0.x + p1.x, p0.y + p1.y, p0.z + p1.z, p0.w + p1.w);
+                        if constexpr (GRP == 4) {
+                            const float4 p2 = *reinterpret_cast<const float4*>(xr + 2 * CH * 16 + u4);
+                            const float4 p3 = *reinterpret_cast<const float4*>(xr + 3 * CH * 16 + u4);
+                            const float4 s2 = make_float4(p2.x + p3.x, p2.y + p3.y, p2.z + p3.z, p2.w + p3.w);
+                            s = make_float4(s.x + s2.x, s.y + s2.y, s.z + s2.z, s.w + s2.w);
+                        }
+                        R[4 * e] = s.x; R[4 * e + 1] = s.y; R[4 * e + 2] = s.z; R[4 * e + 3] = s.w;
+                    }
+                    if (plain) {
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            float u = R[i] + bias;
+                            if (has_res) u += rv[i];
+                            if (acc_r) u += ov[i];
+                            R[i] = u;
+                        }
+                        if (post_div != 1.f) {
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) R[i] = R[i] / post_div;
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) R[i] = S[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        float u = R[i] + bias;
-                        if (relu) u = fmaxf(u, 0.f);
-                        if (has_res) u += rv[i];
-                        u *= scale;
-                        if (acc_r) u += ov[i];
-                        if (post_div != 1.f) u = u / post_div;
-                        R[i] = u;
+                        for (int i = 0; i < NV; ++i) {
+                            float u = R[i] + bias;
+                            if (relu) u = fmaxf(u, 0.f);
+                            if (has_res) u += rv[i];
+                            u *= scale;
+                            if (acc_r) u += ov[i];
+                            if (post_div != 1.f) u = u / post_div;
+                            R[i] = u;
+                        }
                     }
                     if (do_store) {
+                        const int q = q0 + cg + coff;
 #pragma unroll
-                        for (int j = 0; j < NV / 4; ++j) {
+                        for (int j = 0; j < NQ; ++j) {
                             const int qq = q + 4 * j;
                             if (fast || (vec_ok && qq + 3 < a.Tout)) {
                                 *reinterpret_cast<float4*>(yrow + qq) = make_float4(R[4 * j], R[4 * j + 1], R[4 * j + 2], R[4 * j + 3]);
@@ -586,7 +964,6 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                             }
                         }
                     }
-                    }
                 };
 #pragma unroll 1
                 for (int cg = cbeg; cg < cend; cg += 48) {
@@ -594,13 +971,17 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                     if (cg + 16 < cend) group(cg + 16, rB, oB, rA, oA);
                     if (cg + 32 < cend) group(cg + 32, rC, oC, rB, oB);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));
                 if (tid == 0) { if (it == 0) TC3_STAMP(17); if (it == 1) TC3_STAMP(19); if (it == 3) TC3_STAMP(21); }
             }
             if (tid == 0) TC3_STAMP(22);
-        } else
+        } else {
+        // launch-uniform part of the lean-path test (the per-tile part: the tile half lies wholly inside the row)
+        const bool lean_launch = LEAN && ups == 1 && !a.gate && a.split == 0 && !a.relu && !a.ymask && a.scale == 1.f && a.post_div == 1.f &&
+                                 !(STAGED && a.stage) &&
+                                 ((a.y_cs & 3) == 0) && ((a.y_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0) &&
+                                 (!a.res || (((a.res_cs & 3) == 0) && ((a.res_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.res) & 15) == 0)));
+        const bool hres = a.res != nullptr && !(a.dbg & 4), hacc = a.accum != 0 && !(a.dbg & 4), do_st = !(a.dbg & 8);
+        float* const lean_tiles = (!STAGED && a.stage_off > 0 && !(a.dbg & 128)) ? reinterpret_cast<float*>(smem + a.stage_off) : nullptr;
         for (int it = 0; it < my_tiles && ok; ++it) {
             const int buf = it & 1;
             int b, rt, q0;
@@ -609,206 +990,35 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             if (!ok) break;
             tc_fence_after();
             if (tid == 0) { if (it == 0) TC3_STAMP(16); if (it == 1) TC3_STAMP(18); if (it == 3) TC3_STAMP(20); }
-            const int r = rt * MROWS + lq * 32 + lane;             // GEMM row of this lane
-            const bool rok = r < a.Rows;
-            const int rc = rok ? r : a.Rows - 1;
-            const uint32_t dbase = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 128);
+            if (a.dbg & 32) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf)); continue; }   // probe: handshake only
             const int qb = q0 + half * 128;
-            float bias = a.bias[rc];
-            if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + rc);
-            if (a.gate) {
-                // WaveNet gate (wavenet.py:6-13): even lane = tanh argument, odd lane = sigmoid argument of row r/2
-                float* yrow = a.y + (long long)b * a.y_bs + (long long)(rc >> 1) * a.y_cs;
-                const bool vec_ok = ((a.y_cs & 3) == 0) && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0);
-                const bool even = (lane & 1) == 0;
-                for (int cg = 0; cg < 128; cg += 16) {
-                    float v[16];
-                    tmem_ld16(dbase + (uint32_t)cg, v);
-                    const int q = qb + cg;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float u = v[i] + bias;
-                        const float act = even ? tanhf(u) : 1.f / (1.f + expf(-u));
-                        const float other = __shfl_xor_sync(0xffffffffu, act, 1);
-                        v[i] = act * other;
-                    }
-                    if (rok && even) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int qq = q + 4 * j;
-                            if (vec_ok && qq + 3 < a.Tout) *reinterpret_cast<float4*>(yrow + qq) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = v[4 * j + e];
-                            }
-                        }
-                    }
-                }
-            } else if (STAGED && ups == 1 && a.stage && a.split == 0 && qb + 128 <= a.Tout && ((a.y_cs | a.y_bs) & 3) == 0 &&
-                       (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
-                       (!a.res || ((((a.res_cs | a.res_bs) & 3) == 0) && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0))) {
-                // ---- staged epilogue (interior tiles of wide layers).  With lane = row every float4 LDG / STG of the
-                // direct path touches 32 different cache lines; measured, that L1 wavefront time is not hidden
-                // (profiles/r01_tc_grouped_notes.md).  Here each warp transposes its 32 x 16 block through a private
-                // shared tile: global accesses are 8 rows x 64 contiguous bytes per instruction (4x fewer wavefronts),
-                // the residual arrives by cp.async one column group ahead.
-                const int ew = (warp < 4) ? warp : warp - 6;                       // epilogue warp 0..7
-                float* tO = reinterpret_cast<float*>(smem + a.stage_off) + ew * 1280;   // [32][20]
-                float* tR = tO + 640;
-                const int r8 = lane & 7, p4 = lane >> 3;
-                const int Rbase = rt * MROWS + lq * 32 + r8;                        // + 8*i
-                float* ybase = a.y + (long long)b * a.y_bs + (long long)Rbase * a.y_cs + qb + 4 * p4;
-                const float* rbase = (a.res && !(a.dbg & 4)) ? a.res + (long long)b * a.res_bs + (long long)Rbase * a.res_cs + qb + 4 * p4 : nullptr;
-                const bool acc_r = a.accum != 0 && !(a.dbg & 4), mpost_r = a.mask_post != 0, do_store = !(a.dbg & 8);
-                const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
-                float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;   // lane = row view (accumulate loads)
-                auto issue_res = [&](int cg) {
-                    if (!rbase) return;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (Rbase + 8 * i < a.Rows)
-                            cp_async16_zfill(smem_u32(tR + (8 * i + r8) * 20 + 4 * p4), rbase + (long long)(8 * i) * a.res_cs + cg, 16u);
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                };
-                auto prefetch_acc = [&](int cg, float* o_) {
-                    if (!acc_r || !rok) return;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qb + cg + 4 * j));
-                };
-                issue_res(0);
-#pragma unroll 1
-                for (int cg = 0; cg < 128; cg += 16) {
-                    float v[16], ov[16], rv[16];
-                    prefetch_acc(cg, ov);           // accumulate-into-destination (two layers per stage): same-group load
-                    if (rbase) {
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(tR + lane * 20 + 4 * j);
-                            rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w;
-                        }
-                        __syncwarp();
-                        if (cg + 16 < 128) issue_res(cg + 16);
-                    }
-                    tmem_ld16(dbase + (uint32_t)cg, v);
-                    const int q = qb + cg;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float u = v[i] + bias;
-                        if (a.relu) u = fmaxf(u, 0.f);
-                        const float mk = mrow ? __ldg(mrow + q + i) : 1.f;
-                        if (a.mask_pre) u *= mk;
-                        if (rbase) u += rv[i];
-                        u *= a.scale;
-                        if (acc_r) u += ov[i];
-                        if (a.post_div != 1.f) u = u / a.post_div;
-                        if (mpost_r) u *= mk;
-                        v[i] = u;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4*>(tO + lane * 20 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 o4 = *reinterpret_cast<const float4*>(tO + (8 * i + r8) * 20 + 4 * p4);
-                        if (do_store && Rbase + 8 * i < a.Rows) *reinterpret_cast<float4*>(ybase + (long long)(8 * i) * a.y_cs + cg) = o4;
-                    }
-                    __syncwarp();
-                }
-            } else if (ups == 1) {
-                float* yrow = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs;
-                bool acc_r = a.accum != 0, mpost_r = a.mask_post != 0;
-                if (a.split > 0) {          // WaveNet res/skip rows (wavenet.py:108-113)
-                    if (rc < a.split) { acc_r = true; mpost_r = true; }
-                    else { yrow = a.y2 + (long long)b * a.y2_bs + (long long)(rc - a.split) * a.y2_cs; acc_r = a.accum2 != 0; mpost_r = false; }
-                }
-                const float* rrow = a.res ? a.res + (long long)b * a.res_bs + (long long)rc * a.res_cs : nullptr;
-                const float* mrow = a.ymask ? a.ymask + (long long)b * a.ymask_bs : nullptr;
-                const int ycs_eff = (a.split > 0 && rc >= a.split) ? a.y2_cs : a.y_cs;
-                const bool vec_ok = ((ycs_eff & 3) == 0) && (!a.res || (a.res_cs & 3) == 0) &&
-                                    ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0) &&
-                                    (!rrow || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-                // order-enforced software pipeline: the (volatile) loads of group j+1 are issued before the (volatile)
-                // TMEM load of group j, into the OTHER of two register sets -- never copied (a move of a pending load's
-                // result waits for the load and would serialise the groups).  float4 per lane along time (lane = one row).
-                float rA[16], oA[16], rB[16], oB[16];
-                auto prefetch = [&](int cg, float* r_, float* o_) {
-                    const int q = qb + cg;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int qq = q + 4 * j;
-                        if (vec_ok && qq + 3 < a.Tout) {
-                            if (rrow) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r_[4 * j]), "=f"(r_[4 * j + 1]), "=f"(r_[4 * j + 2]), "=f"(r_[4 * j + 3]) : "l"(rrow + qq));
-                            if (acc_r) asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o_[4 * j]), "=f"(o_[4 * j + 1]), "=f"(o_[4 * j + 2]), "=f"(o_[4 * j + 3]) : "l"(yrow + qq));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int qe = min(qq + e, a.Tout - 1);
-                                if (rrow) asm volatile("ld.global.f32 %0, [%1];" : "=f"(r_[4 * j + e]) : "l"(rrow + qe));
-                                if (acc_r) asm volatile("ld.global.f32 %0, [%1];" : "=f"(o_[4 * j + e]) : "l"(yrow + qe));
-                            }
-                        }
-                    }
-                };
-                const bool ld_ok = rok && !(a.dbg & 4), st_ok = rok && !(a.dbg & 8);
-                auto group = [&](int cg, const float* rv, const float* ov, float* rn, float* on) {
-                    float v[16];
-                    if (ld_ok && cg + 16 < 128) prefetch(cg + 16, rn, on);
-                    tmem_ld16(dbase + (uint32_t)cg, v);
-                    const int q = qb + cg;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float u = v[i] + bias;
-                        if (a.relu) u = fmaxf(u, 0.f);
-                        const float mk = mrow ? __ldg(mrow + min(q + i, a.Tout - 1)) : 1.f;
-                        if (a.mask_pre) u *= mk;
-                        if (a.res) u += rv[i];
-                        u *= a.scale;
-                        if (acc_r) u += ov[i];
-                        if (a.post_div != 1.f) u = u / a.post_div;
-                        if (mpost_r) u *= mk;
-                        v[i] = u;
-                    }
-                    if (st_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int qq = q + 4 * j;
-                            if (vec_ok && qq + 3 < a.Tout) {
-                                *reinterpret_cast<float4*>(yrow + qq) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) if (qq + e < a.Tout) yrow[qq + e] = v[4 * j + e];
-                            }
-                        }
-                    }
-                };
-                if (ld_ok) prefetch(0, rA, oA);
-#pragma unroll 1
-                for (int cg = 0; cg < 128; cg += 32) {
-                    group(cg, rA, oA, rB, oB);
-                    group(cg + 16, rB, oB, rA, oA);
-                }
+            if (LEAN && lean_launch && qb + 128 <= a.Tout) {
+                // ---- lean path: every interior tile of the plain layers (bias, optional residual / accumulate).  r02 ncu
+                // source view of the general loop: ~1000 instructions per lane and 16 columns on options that are off, the
+                // eight epilogue warps issue bound.
+                const int r = rt * MROWS + lq * 32 + lane;             // GEMM row of this lane
+                const bool rok = r < a.Rows;
+                const int rc = rok ? r : a.Rows - 1;
+                const uint32_t dbase = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 128);
+                float bias = a.bias[rc];
+                if (a.cond) bias += __ldg(a.cond + (long long)b * a.cond_bs + rc);
+                const bool st_ok = do_st && rok;
+                float* yp = a.y + (long long)b * a.y_bs + (long long)rc * a.y_cs + qb;
+                const float* rp = hres ? a.res + (long long)b * a.res_bs + (long long)rc * a.res_cs + qb : yp;
+                if (lean_tiles) {                                  // transposing variant: coalesced global accesses
+                    float* tO = lean_tiles + ((warp < 4) ? warp : warp - W_EPI2 + 4) * LEAN_TILE_FLOATS;
+                    float* yq = a.y + (long long)b * a.y_bs + qb;
+                    const float* rq = hres ? a.res + (long long)b * a.res_bs + qb : yq;
+                    const int row0 = rt * MROWS + lq * 32;
+                    if (hres) { if (hacc) lean_rows_t<true, true>(dbase, bias, tO, lane, rq, yq, a.res_cs, a.y_cs, row0, a.Rows, do_st);
+                                else lean_rows_t<true, false>(dbase, bias, tO, lane, rq, yq, a.res_cs, a.y_cs, row0, a.Rows, do_st); }
+                    else { if (hacc) lean_rows_t<false, true>(dbase, bias, tO, lane, rq, yq, 0, a.y_cs, row0, a.Rows, do_st);
+                           else lean_rows_t<false, false>(dbase, bias, tO, lane, rq, yq, 0, a.y_cs, row0, a.Rows, do_st); }
+                } else if (hres) { if (hacc) lean_rows<true, true>(dbase, bias, rp, yp, st_ok); else lean_rows<true, false>(dbase, bias, rp, yp, st_ok); }
+                else { if (hacc) lean_rows<false, true>(dbase, bias, rp, yp, st_ok); else lean_rows<false, false>(dbase, bias, rp, yp, st_ok); }
             } else {
-                // polyphase store: row r = co*ups + ph, column q -> y[co][q*ups + ph]; a warp's 32 lanes cover whole
-                // groups of `ups` phases, i.e. contiguous runs of `ups` output samples per channel
-                const int co = rc / ups, ph = rc - co * ups;
-                float* yrow = a.y + (long long)b * a.y_bs + (long long)co * a.y_cs + ph;
-                for (int cg = 0; cg < 128; cg += 16) {
-                    float v[16];
-                    tmem_ld16(dbase + (uint32_t)cg, v);
-                    if (!rok) continue;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int q = qb + cg + i;
-                        float u = v[i] + bias;
-                        if (a.relu) u = fmaxf(u, 0.f);
-                        const long long t = (long long)q * ups;
-                        if (q < a.Tq && t + ph < a.Tout) yrow[t] = u;
-                    }
-                }
+                if constexpr (LEAN) general_tile_call<STAGED>(a, smem, tmem_base, acc_cols, b, rt, q0, buf, lq, half, lane, warp);
+                else general_tile_body<STAGED>(a, smem, tmem_base, acc_cols, b, rt, q0, buf, lq, half, lane, warp);
             }
             tc_fence_before();
             __syncwarp();
@@ -816,26 +1026,26 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             if (tid == 0) { if (it == 0) TC3_STAMP(17); if (it == 1) TC3_STAMP(19); if (it == 3) TC3_STAMP(21); }
         }
         if (tid == 0) TC3_STAMP(22);
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const Tc3Args a) { tc3_body<1, 0>(a); }
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3s_kernel(const Tc3Args a) { tc3_body<1, 0, true>(a); }
-template <int GRP, int DIL>
-__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g_kernel(const Tc3Args a) { tc3_body<GRP, DIL>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3_kernel(const __grid_constant__ Tc3Args a) { tc3_body<1>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3s_kernel(const __grid_constant__ Tc3Args a) { tc3_body<1, true, false>(a); }
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3x_kernel(const __grid_constant__ Tc3Args a) { tc3_body<1, false, false>(a); }   // gate / split / mask / polyphase
+template <int GRP>
+__global__ void __launch_bounds__(NTHREADS2, 1) conv1d_tc3g_kernel(const __grid_constant__ Tc3Args a) { tc3_body<GRP>(a); }
 
 typedef void (*Tc3Kernel)(const Tc3Args);
-// grouped kernel for (tap groups, dilation): dilations 1 / 3 / 5 (the HiFiGAN resblocks) are specialised
-static inline Tc3Kernel grouped_kernel(int grp, int dil) {
-    if (grp == 2) return dil == 1 ? conv1d_tc3g_kernel<2, 1> : dil == 3 ? conv1d_tc3g_kernel<2, 3> : dil == 5 ? conv1d_tc3g_kernel<2, 5> : conv1d_tc3g_kernel<2, 0>;
-    return dil == 1 ? conv1d_tc3g_kernel<4, 1> : dil == 3 ? conv1d_tc3g_kernel<4, 3> : dil == 5 ? conv1d_tc3g_kernel<4, 5> : conv1d_tc3g_kernel<4, 0>;
-}
+// grouped kernel for 2 / 4 tap groups (any dilation with (GRP - 1) * dil <= 15)
+static inline Tc3Kernel grouped_kernel(int grp) { return grp == 2 ? conv1d_tc3g_kernel<2> : conv1d_tc3g_kernel<4>; }
+constexpr int GROUP_XCHG_BYTES = 2 * 2 * 128 * 16 * 4;   // grouped epilogue: per column half two buffers of [128 rows][16] floats
 
 }  // namespace tc3
 }  // namespace b200tts
