@@ -14,7 +14,9 @@ echo "### ncu full, MAS"; ncu --set full --clock-control none -k regex:mas_kerne
 ncu -i gpurun_out/final2/mas2.ncu-rep --page details --csv > gpurun_out/final2/ncu_mas2.details.csv 2>&1
 echo "### stft timing"; python scripts/dev_bench_stft.py 2>&1 | tail -3
 echo "### sanitizer"; (
-for cs in "2 128 700 11 5" "3 64 1004 7 3" "2 32 2000 3 1"; do TC_V3=1 TC_G=1 compute-sanitizer --tool memcheck ./tools/test_conv_tc one $cs 0 2>&1 | grep -E "ERROR SUMMARY|OK|MISMATCH" | tr '\n' ' '; echo " [harness $cs]"; done
-compute-sanitizer --tool memcheck python -m pytest tests/test_ragged_gpu.py tests/test_handoff_gpu.py -x -q 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | tr '\n' ' '; echo " [pytest ragged+handoff memcheck]"
-compute-sanitizer --tool racecheck python -m pytest tests/test_ragged_gpu.py -x -q -k "flow or peak" 2>&1 | grep -E "RACECHECK SUMMARY|passed|failed" | tr '\n' ' '; echo " [pytest racecheck]"
+for cs in "2 128 700 11 5" "3 64 1004 7 3" "2 32 2000 3 1"; do TC_V3=1 TC_G=1 compute-sanitizer --tool memcheck ./tools/test_conv_tc one $cs 0 2>&1 | grep -E "ERROR SUMMARY|OK|MISMATCH" | tr '\n' ' '; echo " [memcheck harness $cs]"; done
+for cs in "2 128 700 11 5" "3 64 1004 7 3" "2 32 2000 3 1"; do TC_V3=1 TC_G=1 compute-sanitizer --tool synccheck ./tools/test_conv_tc one $cs 0 2>&1 | grep -E "ERROR SUMMARY|OK|MISMATCH" | tr '\n' ' '; echo " [synccheck harness $cs]"; done
+compute-sanitizer --tool memcheck python -m pytest tests/test_ragged_gpu.py tests/test_handoff_gpu.py -x -q 2>&1 | grep -E "ERROR SUMMARY|passed|failed" | tr '\n' ' '; echo " [memcheck pytest ragged+handoff]"
+compute-sanitizer --tool racecheck python -m pytest tests/test_handoff_gpu.py tests/test_mas_gpu.py -x -q 2>&1 | grep -E "RACECHECK SUMMARY|passed|failed" | tr '\n' ' '; echo " [racecheck pytest handoff+mas: kernels without tcgen05]"
+for cs in "3 64 1004 7 3" "2 32 2000 3 1" "2 128 700 11 5"; do TC_V3=1 TC_G=1 compute-sanitizer --tool racecheck --print-limit 3 ./tools/test_conv_tc one $cs 0 2>&1 | grep -E "RACECHECK SUMMARY|Race reported|and .* access|OK|MISMATCH" | cut -c1-150 | tr '\n' ' '; echo " [racecheck harness $cs]"; done
 ) > gpurun_out/final2/sanitizer.txt 2>&1; cat gpurun_out/final2/sanitizer.txt

@@ -7,11 +7,16 @@
 // The activation tile keeps the row-shift property (rows are 16 B apart), so tap k is still just a descriptor
 // start-address offset of k*dil rows -- now on the B operand.
 //
-//   warps 4-7        producers : cp.async raw [8 ch][time] windows (4-deep ring) -> leaky-ReLU + hi/lo split -> K-major slabs
-//   warp  8          loader    : per-tap weight blocks {hi,lo}[2 slabs][128 rows][4] by cp.async.bulk (10-deep ring)
-//   warp  9          MMA       : one lane issues 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per tap and chunk, commits to mbarriers
-//   warps 0-3,10-13  epilogue  : lane = output row, columns = time: TMEM -> registers -> float4 global stores (two halves
-//                                of the 256 columns), residual / accumulate loads as float4 with an order-enforced prefetch
+//   warps 0-3, 12-15 epilogue  : two column halves x four TMEM lane quarters.  Plain layers: lean path (TMEM -> + bias ->
+//                                per-warp shared tile -> 8 rows x 64 B global accesses, residual / accumulate loads in that
+//                                mapping one group ahead); everything else: the general path (gate, split, masks, polyphase)
+//   warps 4-9        producers : cp.async raw [8 ch][time] windows (4-deep ring) -> leaky-ReLU + hi/lo split -> K-major slabs
+//                                (5 stages)
+//   warp  10         loader    : per-tap weight blocks {hi,lo}[2 slabs][128 rows][4] by cp.async.bulk, one lane per ring slot
+//                                (6 slots; r02 sweep in profiles/r02_epilogue_instruction_bound.md: 5 activation stages + 6
+//                                weight slots beat 3 + 10 by ~3 %)
+//   warp  11         MMA       : converged warp, one elected lane issues 3 tcgen05.mma (lo*hi, hi*lo, hi*hi) per tap and
+//                                chunk and commits to mbarriers
 //
 // Grouped mode (GRP = 2 / 4) for narrow layers (exactly 64 / 32 output rows, the last two HiFiGAN stages): the 128
 // MMA rows are GRP tap-groups x (128/GRP) channels -- row g * (128/GRP) + c carries the weights of channel c for taps
@@ -42,10 +47,10 @@ constexpr int RAWS = 324;         // raw (cp.async) row stride in floats: the wi
 #define TC3_NRAW 4
 #endif
 #ifndef TC3_NA2
-#define TC3_NA2 3
+#define TC3_NA2 5
 #endif
 #ifndef TC3_NB2
-#define TC3_NB2 10
+#define TC3_NB2 6
 #endif
 constexpr int NRAW = TC3_NRAW;    // raw (cp.async) ring depth
 constexpr int NA2 = TC3_NA2;      // transformed activation stages
@@ -715,7 +720,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
         // One lane per ring slot: lane s owns slot s and feeds it with tap blocks s, s + NB2, s + 2*NB2, ... of this CTA's
         // block sequence.  A single thread walking the ring paid its wait -> expect_tx -> bulk-copy chain (~400 cycles) once
         // per 8 KB block -- measured as a 20 B/clk "L2 limit" that was really this thread (r02 ablation: the kernel without
-        // MMAs still took 75 % of its time).  Ten independent chains keep ten copies in flight.
+        // MMAs still took 75 % of its time).  One independent chain per slot keeps NB2 copies in flight.
         if (lane < NB2) {
             const int total = nchunks * K;                                 // tap blocks per tile (contiguous in memory)
             const long long all = (long long)my_tiles * total;
