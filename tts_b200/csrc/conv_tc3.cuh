@@ -95,7 +95,8 @@ struct Tc3Args {
     int stage;                  // != 0: wide-layer epilogue goes through per-warp shared tiles (coalesced global access)
     int stage_off;              // byte offset of those tiles in dynamic shared memory (8 warps x 5120 B); grouped mode:
                                 // offset of the GROUP_XCHG_BYTES partial-sum exchange tiles
-    int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA, 32 epilogue = handshake only, 64 no test_wait probe, 128 lane = row lean epilogue
+    int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA, 32 epilogue = handshake only, 64 no test_wait probe, 128 lane = row lean epilogue,
+                                // 256 (with 16) the MMA warp arrives on its barriers itself instead of tcgen05.commit (racecheck probe)
     // ---- ragged batches (null lens: every row spans the full tensor).  Row b only has tiles for GEMM columns below
     // min(Tq, lens[b] * rate_q + need_q) and its input is read as zero from min(Tin, lens[b] * rate_in + need_in) on:
     // padded frames cost nothing, and `need` keeps every sample below lens[b] bit-identical to the full computation
@@ -769,6 +770,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             const uint64_t wdesc0 = make_desc(smem_u32(smB), slabB);
             const uint32_t bfull0 = BAR(B_FULL), bempty0 = BAR(B_EMPTY);
             const bool no_mma = (a.dbg & 16) != 0;
+            const bool thread_arrive = no_mma && (a.dbg & 256) != 0;                       // sanitizer probe: plain mbarrier arrivals
             const bool no_probe = (a.dbg & 64) != 0;                                       // every weight barrier through try_wait
             bool ok = true;
             int sa = 0; uint32_t pa = 0;                                                  // activation stage / its parity
@@ -805,7 +807,7 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                                 mma_tf32(dcol, w_lo, xh, idesc, 1u);
                                 mma_tf32(dcol, w_hi, xh, idesc, 1u);
                             }
-                            mma_commit(bempty);
+                            if (thread_arrive) mbar_arrive(bempty); else mma_commit(bempty);
                         }
                         acc = 1u;
                         xh += xstep; xl += xstep;
@@ -814,10 +816,10 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         bfull = nfull; pb = npb;
                         have = __all_sync(0xffffffffu, have_next);                        // keep the warp's control flow uniform
                     }
-                    if (ok && leader) mma_commit(BAR(A_EMPTY + sa));
+                    if (ok && leader) { if (thread_arrive) mbar_arrive(BAR(A_EMPTY + sa)); else mma_commit(BAR(A_EMPTY + sa)); }
                     if (++sa == NA2) { sa = 0; pa ^= 1u; }
                 }
-                if (ok && leader) mma_commit(BAR(ACC_FULL + buf));
+                if (ok && leader) { if (thread_arrive) mbar_arrive(BAR(ACC_FULL + buf)); else mma_commit(BAR(ACC_FULL + buf)); }
                 if (lane == 0) { if (it == 0) TC3_STAMP(8); if (it == 1) TC3_STAMP(9); if (it == 3) TC3_STAMP(10); }
             }
             if (lane == 0) TC3_STAMP(11);
