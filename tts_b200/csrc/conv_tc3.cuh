@@ -770,7 +770,11 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
             const uint64_t wdesc0 = make_desc(smem_u32(smB), slabB);
             const uint32_t bfull0 = BAR(B_FULL), bempty0 = BAR(B_EMPTY);
             const bool no_mma = (a.dbg & 16) != 0;
-            const bool thread_arrive = no_mma && (a.dbg & 256) != 0;                       // sanitizer probe: plain mbarrier arrivals
+#ifdef TC3_RACE_PROBE      // harness-only sanitizer probe (tools/r2u.sh): plain mbarrier arrivals instead of tcgen05.commit
+            const bool thread_arrive = no_mma && (a.dbg & 256) != 0;
+#else
+            constexpr bool thread_arrive = false;
+#endif
             const bool no_probe = (a.dbg & 64) != 0;                                       // every weight barrier through try_wait
             bool ok = true;
             int sa = 0; uint32_t pa = 0;                                                  // activation stage / its parity
