@@ -96,7 +96,7 @@ struct Tc3Args {
     int stage_off;              // byte offset of those tiles in dynamic shared memory (8 warps x 5120 B); grouped mode:
                                 // offset of the GROUP_XCHG_BYTES partial-sum exchange tiles
     int dbg;                    // harness-only bottleneck probes: 1 no cp.async, 2 no transform, 4 no epilogue loads, 8 no stores, 16 no MMA, 32 epilogue = handshake only, 64 no test_wait probe, 128 lane = row lean epilogue,
-                                // 256 (with 16) the MMA warp arrives on its barriers itself instead of tcgen05.commit (racecheck probe)
+                                // 512 full-width MMAs on partial tiles, 256 (with 16) the MMA warp arrives on its barriers itself instead of tcgen05.commit (racecheck probe)
     // ---- ragged batches (null lens: every row spans the full tensor).  Row b only has tiles for GEMM columns below
     // min(Tq, lens[b] * rate_q + need_q) and its input is read as zero from min(Tin, lens[b] * rate_in + need_in) on:
     // padded frames cost nothing, and `need` keeps every sample below lens[b] bit-identical to the full computation
@@ -137,6 +137,12 @@ __device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t* r) {   
     else
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
 }
+// 16 columns x 32 lanes of zeros into TMEM (kernel start: stale accumulator columns must at least be finite, see the MMA warp)
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -556,10 +562,24 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (GRP == 1) {
+        // Partial tiles issue MMAs over their valid columns only (MMA warp), so the epilogue can read accumulator columns
+        // that no MMA of this launch wrote.  They are never consumed, but they may be stored past a row's extent and are
+        // multiplied by the zero mask in the flow: make sure they are finite -- zero both accumulator buffers once.
+        if (warp < 4 || warp >= W_EPI2) {
+            const uint32_t zl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >= W_EPI2 ? 1 : 0) * 128);
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 16) { tmem_st16_zero(zl + (uint32_t)c); tmem_st16_zero(zl + (uint32_t)(TT2 + c)); }
+            tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (tid == 0) TC3_STAMP(0);
     // Programmatic dependent launch: the next layer's CTAs may take SMs as this grid drains (they park in their own
     // griddepcontrol.wait); every role that touches activations waits for the previous layer here.  The weight loader
-    // (warp 8) reads only constants and starts filling its ring at once.
+    // (warp W_LOAD) reads only constants and starts filling its ring at once.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp != W_LOAD) asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -789,6 +809,25 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + (uint32_t)buf * acc_cols;
                 uint32_t acc = 0u;
+                // The last tile of a row is on average half empty (the single tile of a flow / conv_pre row even more): its
+                // MMAs cover only the columns that hold data, N = 16 * ceil(valid / 16).  Columns beyond stay stale in TMEM;
+                // the epilogue may store them past the row's extent, where no consumer reads (consumer extents <= producer
+                // extents by construction of the margins) and the final waveform tail is zero-filled by conv_post.
+                uint32_t idesc_t = idesc;
+                if constexpr (GRP == 1) {
+                    if (!(a.dbg & 512)) {
+                        int b_, rt_, q0_;
+                        decode(it, b_, rt_, q0_);
+                        long long ext = a.Tq;
+                        if (ragged) {
+                            const long long e = (long long)a.lens[b_] * a.rate_q + a.need_q;
+                            ext = e < (long long)a.Tq ? (e > 0 ? e : 0) : (long long)a.Tq;
+                        }
+                        int n = ((int)ext - q0_ + 15) & ~15;
+                        n = n < 16 ? 16 : (n > TT2 ? TT2 : n);
+                        idesc_t = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(n >> 3) << 17);
+                    }
+                }
                 for (int c = 0; c < nchunks && ok; ++c) {
                     ok = mbar_wait(BAR(A_FULL + sa), pa, a.err);
                     if (!ok) break;
@@ -807,9 +846,9 @@ __device__ __forceinline__ void tc3_body(const Tc3Args& a) {
                         const uint64_t w_hi = wdesc, w_lo = wdesc + wlo_off;
                         if (leader) {
                             if (!no_mma) {
-                                mma_tf32(dcol, w_hi, xl, idesc, acc);                     // small terms first
-                                mma_tf32(dcol, w_lo, xh, idesc, 1u);
-                                mma_tf32(dcol, w_hi, xh, idesc, 1u);
+                                mma_tf32(dcol, w_hi, xl, idesc_t, acc);                   // small terms first
+                                mma_tf32(dcol, w_lo, xh, idesc_t, 1u);
+                                mma_tf32(dcol, w_hi, xh, idesc_t, 1u);
                             }
                             if (thread_arrive) mbar_arrive(bempty); else mma_commit(bempty);
                         }
